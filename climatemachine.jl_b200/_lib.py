@@ -1,0 +1,104 @@
+"""ctypes binding of libcmdg (include/cmdg.h).  Fails loudly if the CUDA library is missing:
+there is no CPU or PyTorch fallback for the DG tendency path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmdg.so")
+
+CMDG_F32, CMDG_F64 = 4, 8
+MODEL_ATMOS_DRY, MODEL_HB = 1, 2
+NF_RUSANOV, NF_CENTRAL, NF_ROE = 0, 1, 2
+ORIENT_NONE, ORIENT_FLAT, ORIENT_SPHERICAL = 0, 1, 2
+REF_NONE, REF_HYDROSTATIC = 0, 1
+TURB_CONSTANT_KINEMATIC, TURB_CONSTANT_DYNAMIC, TURB_SMAGORINSKY = 0, 1, 2
+SRC_GRAVITY, SRC_CORIOLIS = 1, 2
+BC_FREESLIP, BC_NOSLIP = 1, 2
+DIR_EVERY, DIR_HORIZONTAL = 0, 1
+
+ERRORS = {-1: "CMDG_ERR_INVALID", -2: "CMDG_ERR_UNSUPPORTED", -3: "CMDG_ERR_CUDA",
+          -4: "CMDG_ERR_NCCL", -5: "CMDG_ERR_NODEVICE"}
+
+
+class cmdg_desc(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("float_bytes", C.c_int32), ("dim", C.c_int32),
+        ("N", C.c_int32), ("nelem", C.c_int64), ("nrealelem", C.c_int64),
+        ("nvertelem", C.c_int32), ("model", C.c_int32), ("nf_first", C.c_int32),
+        ("nf_second", C.c_int32), ("nf_gradient", C.c_int32), ("orientation", C.c_int32),
+        ("ref_state", C.c_int32), ("subtract_off", C.c_int32), ("turbulence", C.c_int32),
+        ("turb_with_divergence", C.c_int32), ("turb_param", C.c_double),
+        ("sources", C.c_int32), ("diffusion_direction", C.c_int32),
+        ("skip_zero_viscosity", C.c_int32), ("write_aux_diagnostics", C.c_int32),
+        ("nbc", C.c_int32), ("bc_kind", C.c_int32 * 6),
+        ("nstate", C.c_int32), ("naux", C.c_int32), ("ngrad", C.c_int32),
+        ("ngradflux", C.c_int32),
+        ("R_d", C.c_double), ("cp_d", C.c_double), ("cv_d", C.c_double), ("T_0", C.c_double),
+        ("MSLP", C.c_double), ("grav", C.c_double), ("Omega", C.c_double),
+        ("inv_Pr_turb", C.c_double),
+    ]
+
+
+class CmdgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/cmdg.h declares
+SYMBOLS = [
+    "cmdg_version", "cmdg_last_error", "cmdg_create", "cmdg_destroy", "cmdg_bind_grid",
+    "cmdg_bind_state", "cmdg_tendency", "cmdg_lsrk_update", "cmdg_lsrk_steps",
+    "cmdg_lsrk_steps_host", "cmdg_comm_unique_id", "cmdg_comm_init", "cmdg_exchange_begin",
+    "cmdg_exchange_end", "cmdg_sync", "cmdg_kernel_launches", "cmdg_set_timing",
+    "cmdg_last_kernel_ms",
+]
+
+
+def lib():
+    """Load libcmdg.so (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CmdgError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'`.  The DG tendency path has no CPU/PyTorch fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.cmdg_version.restype = C.c_int
+    L.cmdg_last_error.restype = C.c_char_p
+    L.cmdg_last_error.argtypes = [vp]
+    L.cmdg_create.argtypes = [C.POINTER(cmdg_desc), C.POINTER(vp)]
+    L.cmdg_destroy.argtypes = [vp]
+    L.cmdg_bind_grid.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, i64,
+                                 C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), i32]
+    L.cmdg_bind_state.argtypes = [vp, vp, vp]
+    L.cmdg_tendency.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
+    L.cmdg_lsrk_update.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
+    L.cmdg_lsrk_steps.argtypes = [vp, vp, vp, dbl, dbl, i32, C.POINTER(dbl), C.POINTER(dbl),
+                                  C.POINTER(dbl), i64, vp]
+    L.cmdg_lsrk_steps_host.argtypes = [vp, vp, dbl, dbl, i32, C.POINTER(dbl), C.POINTER(dbl),
+                                       C.POINTER(dbl), i64]
+    L.cmdg_comm_unique_id.argtypes = [vp]
+    L.cmdg_comm_init.argtypes = [vp, vp, i32, i32]
+    L.cmdg_exchange_begin.argtypes = [vp, vp, i32, vp]
+    L.cmdg_exchange_end.argtypes = [vp, vp, i32, vp]
+    L.cmdg_sync.argtypes = [vp]
+    L.cmdg_kernel_launches.argtypes = [vp]
+    L.cmdg_kernel_launches.restype = i64
+    L.cmdg_set_timing.argtypes = [vp, i32]
+    L.cmdg_last_kernel_ms.argtypes = [vp, C.POINTER(i64)]
+    L.cmdg_last_kernel_ms.restype = dbl
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("cmdg_version",):
+            pass
+    _lib = L
+    return L
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = lib().cmdg_last_error(handle)
+        raise CmdgError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")

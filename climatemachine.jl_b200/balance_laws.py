@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's model/numerical-flux type tags for the hot path.
+
+These records carry exactly what the reference encodes in Julia types and what libcmdg's
+``cmdg_desc`` needs (include/cmdg.h):
+
+* ``AtmosModel`` / ``AtmosPhysics`` / ``AtmosProblem``  <- src/Atmos/Model/AtmosModel.jl:110-377,
+  src/Atmos/Model/problem.jl:13-37
+* ``NoOrientation, FlatOrientation, SphericalOrientation`` <- src/Common/Orientations/Orientations.jl
+* ``NoReferenceState, HydrostaticState, DecayingTemperatureProfile`` <- src/Atmos/Model/ref_state.jl:22-64
+* ``ConstantDynamicViscosity, ConstantKinematicViscosity, SmagorinskyLilly``
+  <- src/Common/TurbulenceClosures/TurbulenceClosures.jl:287-420
+* ``Gravity, Coriolis`` <- src/Atmos/Model/tendencies_momentum.jl:62-92
+* ``AtmosBC, Impenetrable, FreeSlip, NoSlip, Insulating`` <- src/Atmos/Model/boundaryconditions.jl:34-55
+* ``RusanovNumericalFlux, CentralNumericalFluxFirstOrder, RoeNumericalFlux,
+  CentralNumericalFluxSecondOrder, CentralNumericalFluxGradient``
+  <- src/Numerics/DGMethods/NumericalFluxes.jl
+* ``EarthParameterSet`` <- CLIMAParameters.jl 0.2.0 (un-vendored; values restated)
+
+Anything outside the supported set raises ``UnsupportedModelError`` -- there is no fallback.
+"""
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+
+class UnsupportedModelError(NotImplementedError):
+    pass
+
+
+@dataclass(frozen=True)
+class EarthParameterSet:
+    gas_constant: float = 8.3144598
+    molmass_dryair: float = 28.97e-3
+    kappa_d: float = 2 / 7
+    T_0: float = 273.16
+    MSLP: float = 1.01325e5
+    grav: float = 9.81
+    Omega: float = 7.2921159e-5
+    planet_radius: float = 6.371e6
+    inv_Pr_turb: float = 3.0
+    C_smag: float = 0.21
+    T_surf_ref: float = 290.0
+    T_min_ref: float = 220.0
+
+    @property
+    def R_d(self):
+        return self.gas_constant / self.molmass_dryair
+
+    @property
+    def cp_d(self):
+        return self.R_d / self.kappa_d
+
+    @property
+    def cv_d(self):
+        return self.cp_d - self.R_d
+
+
+# --- orientations ----------------------------------------------------------
+class NoOrientation:
+    pass
+
+
+class FlatOrientation:
+    pass
+
+
+class SphericalOrientation:
+    pass
+
+
+# --- reference states ------------------------------------------------------
+class NoReferenceState:
+    pass
+
+
+@dataclass(frozen=True)
+class DecayingTemperatureProfile:
+    T_virt_surf: float = 290.0
+    T_min_ref: float = 220.0
+    H_t: float = 8.0e3
+
+
+@dataclass(frozen=True)
+class HydrostaticState:
+    virtual_temperature_profile: DecayingTemperatureProfile
+    relative_humidity: float = 0.0
+    subtract_off: bool = True
+
+
+# --- turbulence closures ---------------------------------------------------
+@dataclass(frozen=True)
+class ConstantDynamicViscosity:
+    ρν: float = 0.0
+    with_divergence: bool = False
+
+
+@dataclass(frozen=True)
+class ConstantKinematicViscosity:
+    ν: float = 0.0
+    with_divergence: bool = False
+
+
+@dataclass(frozen=True)
+class SmagorinskyLilly:
+    C_smag: float = 0.21
+
+
+# --- sources ---------------------------------------------------------------
+class Gravity:
+    pass
+
+
+class Coriolis:
+    pass
+
+
+# --- boundary conditions ---------------------------------------------------
+class FreeSlip:
+    pass
+
+
+class NoSlip:
+    pass
+
+
+@dataclass(frozen=True)
+class Impenetrable:
+    drag: object = field(default_factory=FreeSlip)
+
+
+class Insulating:
+    pass
+
+
+@dataclass(frozen=True)
+class AtmosBC:
+    momentum: Impenetrable = field(default_factory=Impenetrable)
+    energy: object = field(default_factory=Insulating)
+
+
+# --- moisture --------------------------------------------------------------
+class DryModel:
+    pass
+
+
+# --- numerical fluxes ------------------------------------------------------
+class RusanovNumericalFlux:
+    pass
+
+
+class CentralNumericalFluxFirstOrder:
+    pass
+
+
+class RoeNumericalFlux:
+    pass
+
+
+class CentralNumericalFluxSecondOrder:
+    pass
+
+
+class CentralNumericalFluxGradient:
+    pass
+
+
+# --- directions ------------------------------------------------------------
+class EveryDirection:
+    pass
+
+
+class HorizontalDirection:
+    pass
+
+
+@dataclass
+class AtmosModel:
+    """Dry, compressible, total-energy AtmosModel (the subset libcmdg compiles in)."""
+    param_set: EarthParameterSet = field(default_factory=EarthParameterSet)
+    orientation: object = field(default_factory=NoOrientation)
+    ref_state: object = field(default_factory=NoReferenceState)
+    turbulence: object = field(default_factory=ConstantDynamicViscosity)
+    moisture: object = field(default_factory=DryModel)
+    source: Tuple = ()
+    boundaryconditions: Tuple = ()
+    # anything else the reference's AtmosModel can hold is unsupported here
+    hyperdiffusion: Optional[object] = None
+    precipitation: Optional[object] = None
+    radiation: Optional[object] = None
+    tracers: Optional[object] = None
+    turbconv: Optional[object] = None
+
+    def number_states(self, kind):
+        smag = isinstance(self.turbulence, SmagorinskyLilly)
+        if kind == "Prognostic":
+            return 5
+        if kind == "Gradient":
+            return 5 if smag else 4
+        if kind == "GradientFlux":
+            return 10 if smag else 9
+        if kind == "Auxiliary":
+            c = 3
+            if not isinstance(self.orientation, NoOrientation):
+                c += 4
+            if isinstance(self.ref_state, HydrostaticState):
+                c += 7
+            if smag:
+                c += 1
+            return c + 2
+        raise KeyError(kind)
+
+    def validate(self):
+        for name in ("hyperdiffusion", "precipitation", "radiation", "tracers", "turbconv"):
+            if getattr(self, name) is not None:
+                raise UnsupportedModelError(
+                    f"AtmosModel.{name} = {getattr(self, name)!r} is not supported by libcmdg "
+                    "(dry compressible Euler / Navier-Stokes subset only); no fallback exists")
+        if not isinstance(self.moisture, DryModel):
+            raise UnsupportedModelError("only DryModel moisture is supported")
+        for s in self.source:
+            if not isinstance(s, (Gravity, Coriolis)):
+                raise UnsupportedModelError(f"unsupported source {type(s).__name__}")
+        for bc in self.boundaryconditions:
+            if not (isinstance(bc, AtmosBC) and isinstance(bc.momentum, Impenetrable)
+                    and isinstance(bc.momentum.drag, (FreeSlip, NoSlip))
+                    and isinstance(bc.energy, Insulating)):
+                raise UnsupportedModelError(f"unsupported boundary condition {bc!r}")

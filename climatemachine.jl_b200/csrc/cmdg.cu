@@ -1,0 +1,815 @@
+// cmdg.cu -- host side of libcmdg: C ABI (include/cmdg.h), handle lifecycle, packed private
+// geometry, kernel dispatch, low-storage RK driver and the NCCL halo exchange.
+//
+// Reference call stack replaced (ClimateMachine.jl):
+//   dostep!  (ODESolvers/LowStorageRungeKuttaMethod.jl:102-144)
+//     -> (dg::DGModel)(tendency, Q, p, t, alpha, beta)   (DGMethods/DGModel.jl:85-427)
+//          begin_ghost_exchange! / end_ghost_exchange!   (Arrays/MPIStateArrays.jl:411-483)
+//          launch_volume_gradients!, launch_interface_gradients!,
+//          launch_volume_tendency!, launch_interface_tendency!  (DGMethods/SpaceDiscretization.jl)
+//     -> update!                                         (LowStorageRungeKuttaMethod.jl:146-158)
+#include "../../include/cmdg.h"
+#include "cmdg_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cmdg;
+
+namespace {
+
+std::string g_create_error;
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    // torch ships its own libnccl.so.2; if it is already mapped, dlopen by soname returns it
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      err = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return false;
+    }
+#define CMDG_SYM(field, name)                                   \
+  field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); \
+  if (!field) {                                                 \
+    err = std::string("libnccl misses symbol ") + name;         \
+    return false;                                               \
+  }
+    CMDG_SYM(GetUniqueId, "ncclGetUniqueId");
+    CMDG_SYM(CommInitRank, "ncclCommInitRank");
+    CMDG_SYM(CommDestroy, "ncclCommDestroy");
+    CMDG_SYM(GroupStart, "ncclGroupStart");
+    CMDG_SYM(GroupEnd, "ncclGroupEnd");
+    CMDG_SYM(Send, "ncclSend");
+    CMDG_SYM(Recv, "ncclRecv");
+    CMDG_SYM(GetErrorString, "ncclGetErrorString");
+#undef CMDG_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct cmdg_handle_s {
+  cmdg_desc d{};
+  std::string err;
+  int Nq = 0, Np = 0, Nfp = 0;
+  size_t fb = 8;  // bytes per float
+  bool aux_model = false, visc = false;
+  // caller-owned device arrays
+  void *aux = nullptr, *gradflux = nullptr;
+  // private device buffers
+  void *vgeoP = nullptr, *sgeoP = nullptr, *Ddev = nullptr;
+  int2 *conn = nullptr;
+  int *interior = nullptr, *exterior = nullptr;
+  int64_t ninterior = 0, nexterior = 0;
+  int64_t *vmapsend0 = nullptr, *vmaprecv0 = nullptr;
+  int64_t nvmapsend = 0, nvmaprecv = 0;
+  std::vector<int> nabrtorank;
+  std::vector<int64_t> sendrange, recvrange;  // 0-based [first, last) pairs
+  void *sendbuf = nullptr, *recvbuf = nullptr;
+  size_t commbuf_states = 0;
+  void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
+  void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
+  bool grid_bound = false;
+  // communication
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  bool exchange_open = false;
+  // bookkeeping
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
+  double last_ms = -1;
+  int64_t last_nl = 0;
+};
+
+namespace {
+
+int fail(cmdg_handle h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(h, CMDG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#define NC(call)                                                                            \
+  do {                                                                                      \
+    ncclResult_t r_ = (call);                                                               \
+    if (r_ != ncclSuccess)                                                                  \
+      return fail(h, CMDG_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+template <class R>
+AtmosParams<R> make_params(const cmdg_handle_s *h) {
+  const cmdg_desc &d = h->d;
+  AtmosParams<R> P{};
+  P.R_d = (R)d.R_d;
+  P.cp_d = (R)d.cp_d;
+  P.cv_d = (R)d.cv_d;
+  P.T_0 = (R)d.T_0;
+  P.MSLP = (R)d.MSLP;
+  P.grav = (R)d.grav;
+  P.two_Omega = (R)(2 * (R)d.Omega);
+  P.inv_Pr_turb = (R)d.inv_Pr_turb;
+  P.gamma = P.cp_d / P.cv_d;
+  P.inv_cv = R(1) / P.cv_d;
+  P.kappa = P.R_d / P.cp_d;
+  P.turb_param = (R)d.turb_param;
+  P.turbulence = d.turbulence;
+  P.with_divergence = d.turb_with_divergence;
+  P.sources = d.sources;
+  P.subtract_off = (d.ref_state == CMDG_REF_HYDROSTATIC) && d.subtract_off;
+  P.horizontal_diffusion = d.diffusion_direction == CMDG_DIR_HORIZONTAL;
+  for (int i = 0; i < 6; ++i) P.bc_kind[i] = d.bc_kind[i];
+  // auxiliary layout, vars_state(::AtmosModel, ::Auxiliary) (AtmosModel.jl:479-497)
+  int c = 3;
+  P.a_Phi = P.a_gradPhi = P.a_ref_rho = P.a_ref_p = P.a_Delta = -1;
+  if (d.orientation != CMDG_ORIENT_NONE) {
+    P.a_Phi = c;
+    P.a_gradPhi = c + 1;
+    c += 4;
+  }
+  if (d.ref_state == CMDG_REF_HYDROSTATIC) {
+    P.a_ref_rho = c;
+    P.a_ref_p = c + 1;
+    c += 7;
+  }
+  if (d.turbulence == CMDG_TURB_SMAGORINSKY) P.a_Delta = c++;
+  P.a_theta_v = c;
+  P.a_T = c + 1;
+  P.naux = c + 2;
+  P.ngradflux = d.ngradflux;
+  return P;
+}
+
+int expected_naux(const cmdg_desc &d) {
+  int c = 3;
+  if (d.orientation != CMDG_ORIENT_NONE) c += 4;
+  if (d.ref_state == CMDG_REF_HYDROSTATIC) c += 7;
+  if (d.turbulence == CMDG_TURB_SMAGORINSKY) c += 1;
+  return c + 2;
+}
+
+cudaEvent_t timing_event(cmdg_handle h) {
+  if (h->tev_used == h->tev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->tev.push_back(e);
+  }
+  return h->tev[h->tev_used++];
+}
+
+template <class R, int NQ, int NF1, bool AUX, bool VISC>
+int launch_tend_inst(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P, int64_t n,
+                     cudaStream_t st) {
+  using SM = TendSmem<R, NQ, AUX, VISC>;
+  auto kern = dg_tendency_kernel<R, NQ, NF1, AUX, VISC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    attr_set = true;
+  }
+  if (h->timing) cudaEventRecord(timing_event(h), st);
+  kern<<<(unsigned)n, Dims<NQ>::BLOCK, sizeof(SM), st>>>(a, P);
+  if (h->timing) cudaEventRecord(timing_event(h), st);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+template <class R, int NQ, int NF1>
+int launch_tend_nf(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P, int64_t n,
+                   cudaStream_t st) {
+  if (h->aux_model) {
+    if (h->visc) return launch_tend_inst<R, NQ, NF1, true, true>(h, a, P, n, st);
+    return launch_tend_inst<R, NQ, NF1, true, false>(h, a, P, n, st);
+  }
+  if (h->visc) return launch_tend_inst<R, NQ, NF1, false, true>(h, a, P, n, st);
+  return launch_tend_inst<R, NQ, NF1, false, false>(h, a, P, n, st);
+}
+
+template <class R>
+int launch_tendency(cmdg_handle h, const TendArgs<R> &a, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const AtmosParams<R> P = make_params<R>(h);
+  switch (h->d.nf_first) {
+    case CMDG_NF_RUSANOV: return launch_tend_nf<R, 5, NF_RUSANOV>(h, a, P, n, st);
+    case CMDG_NF_CENTRAL: return launch_tend_nf<R, 5, NF_CENTRAL>(h, a, P, n, st);
+    case CMDG_NF_ROE: return launch_tend_nf<R, 5, NF_ROE>(h, a, P, n, st);
+  }
+  return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported first-order numerical flux");
+}
+
+template <class R>
+int launch_gradient(cmdg_handle h, const GradArgs<R> &a, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const AtmosParams<R> P = make_params<R>(h);
+  if (h->aux_model)
+    dg_gradient_kernel<R, 5, true><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  else
+    dg_gradient_kernel<R, 5, false><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// halo exchange (MPIStateArrays.jl:411-514)
+// ------------------------------------------------------------------------------------
+template <class R>
+int exchange_begin_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
+  if (!h->comm || h->nabrtorank.empty()) return 0;
+  if (h->exchange_open) return fail(h, CMDG_ERR_INVALID,
+                                    "The current ghost exchange must end before another begins.");
+  if ((size_t)nstate > h->commbuf_states) {
+    if (h->sendbuf) cudaFree(h->sendbuf);
+    if (h->recvbuf) cudaFree(h->recvbuf);
+    CU(cudaMalloc(&h->sendbuf, (size_t)h->nvmapsend * nstate * sizeof(R) + 16));
+    CU(cudaMalloc(&h->recvbuf, (size_t)h->nvmaprecv * nstate * sizeof(R) + 16));
+    h->commbuf_states = nstate;
+  }
+  // kernel_fillsendbuf! on the compute stream, then hand over to the comm stream
+  if (h->nvmapsend > 0) {
+    pack_kernel<R><<<(unsigned)((h->nvmapsend + 255) / 256), 256, 0, st>>>(
+        (R *)h->sendbuf, (const R *)array, h->vmapsend0, h->nvmapsend, h->Np, nstate);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  CU(cudaEventRecord(h->ev_ready, st));
+  CU(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  NC(g_nccl.GroupStart());
+  for (size_t n = 0; n < h->nabrtorank.size(); ++n) {
+    const int64_t r0 = h->recvrange[2 * n], r1 = h->recvrange[2 * n + 1];
+    const int64_t s0 = h->sendrange[2 * n], s1 = h->sendrange[2 * n + 1];
+    NC(g_nccl.Recv((char *)h->recvbuf + (size_t)r0 * nstate * sizeof(R),
+                   (size_t)(r1 - r0) * nstate * sizeof(R), ncclInt8, h->nabrtorank[n], h->comm,
+                   h->comm_stream));
+    NC(g_nccl.Send((const char *)h->sendbuf + (size_t)s0 * nstate * sizeof(R),
+                   (size_t)(s1 - s0) * nstate * sizeof(R), ncclInt8, h->nabrtorank[n], h->comm,
+                   h->comm_stream));
+  }
+  NC(g_nccl.GroupEnd());
+  CU(cudaEventRecord(h->ev_done, h->comm_stream));
+  h->exchange_open = true;
+  return 0;
+}
+
+template <class R>
+int exchange_end_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
+  if (!h->comm || h->nabrtorank.empty()) return 0;
+  if (!h->exchange_open)
+    return fail(h, CMDG_ERR_INVALID, "A ghost exchange must begin before it ends.");
+  CU(cudaStreamWaitEvent(st, h->ev_done, 0));
+  if (h->nvmaprecv > 0) {
+    unpack_kernel<R><<<(unsigned)((h->nvmaprecv + 255) / 256), 256, 0, st>>>(
+        (R *)array, (const R *)h->recvbuf, h->vmaprecv0, h->nvmaprecv, h->Np, nstate);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  h->exchange_open = false;
+  return 0;
+}
+
+template <class R>
+TendArgs<R> base_args(cmdg_handle h) {
+  TendArgs<R> a{};
+  a.aux = (const R *)h->aux;
+  a.gradflux = (const R *)h->gradflux;
+  a.vgeoP = (const R *)h->vgeoP;
+  a.sgeoP = (const R *)h->sgeoP;
+  a.conn = h->conn;
+  a.D = (const R *)h->Ddev;
+  a.aux_out = h->d.write_aux_diagnostics ? (R *)h->aux : nullptr;
+  return a;
+}
+
+// One full evaluation in the reference's order (DGModel.jl:85-427).  With `Qout` set the
+// stage update is fused (cmdg_lsrk_steps); the exchange schedule is then exterior-first, so
+// that the halo of the *next* stage's state is in flight while the interior elements of this
+// stage are computed.
+template <class R>
+int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double beta,
+               cudaStream_t st) {
+  const bool par = h->comm && !h->nabrtorank.empty();
+  const int64_t nreal = h->d.nrealelem;
+  TendArgs<R> a = base_args<R>(h);
+  a.Q = (const R *)Q;
+  a.dQ = (R *)dQ;
+  a.Qout = nullptr;
+  a.alpha = (R)alpha;
+  a.beta = (R)beta;
+  a.t = (R)t;
+  GradArgs<R> ga{(const R *)Q, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
+                 (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev};
+  int rc;
+  if (!par) {
+    if (h->visc) {
+      ga.elems = nullptr;
+      if ((rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+    }
+    a.elems = nullptr;
+    return launch_tendency<R>(h, a, nreal, st);
+  }
+  if ((rc = exchange_begin_t<R>(h, Q, h->d.nstate, st))) return rc;
+  if (h->visc) {
+    ga.elems = h->interior;
+    if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, Q, h->d.nstate, st))) return rc;
+    ga.elems = h->exterior;
+    if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+  }
+  a.elems = h->interior;
+  if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
+  if (h->visc) {
+    if ((rc = exchange_end_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+  } else {
+    if ((rc = exchange_end_t<R>(h, Q, h->d.nstate, st))) return rc;
+  }
+  a.elems = h->exterior;
+  return launch_tendency<R>(h, a, h->nexterior, st);
+}
+
+template <class R>
+int lsrk_update_t(cmdg_handle h, void *dQ, void *Q, double rka, double rkb, double dt,
+                  cudaStream_t st) {
+  const size_t n = (size_t)h->d.nrealelem * h->d.nstate * h->Np;
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+  lsrk_update_kernel<R><<<blocks, 256, 0, st>>>((R *)dQ, (R *)Q, (R)rka, (R)rkb, (R)dt, n);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+template <class R>
+int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nstage,
+                 const double *rka, const double *rkb, const double *rkc, int64_t nsteps,
+                 cudaStream_t st) {
+  const bool par = h->comm && !h->nabrtorank.empty();
+  const int64_t nreal = h->d.nrealelem;
+  const size_t bytes = (size_t)h->d.nelem * h->d.nstate * h->Np * sizeof(R);
+  if (!h->Qtmp) CU(cudaMalloc(&h->Qtmp, bytes));
+  R *cur = (R *)Q, *nxt = (R *)h->Qtmp;
+  if (par) {
+    // ghosts of the initial state
+    int rc;
+    if ((rc = exchange_begin_t<R>(h, cur, h->d.nstate, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, cur, h->d.nstate, st))) return rc;
+  }
+  h->tev_used = 0;
+  for (int64_t step = 0; step < nsteps; ++step) {
+    const double time = t0 + (double)step * dt;
+    for (int s = 0; s < nstage; ++s) {
+      TendArgs<R> a = base_args<R>(h);
+      a.Q = cur;
+      a.dQ = (R *)dQ;
+      a.Qout = nxt;
+      a.alpha = R(1);
+      a.beta = (R)rka[s];
+      a.rkb_dt = (R)((R)rkb[s] * (R)dt);
+      a.t = (R)(time + rkc[s] * dt);
+      // aux diagnostics are refreshed by the last stage only (they are read after steps)
+      if (s != nstage - 1) a.aux_out = nullptr;
+      GradArgs<R> ga{cur, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
+                     (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev};
+      int rc;
+      if (!par) {
+        if (h->visc && (rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+        a.elems = nullptr;
+        if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
+      } else {
+        if (h->visc) {
+          ga.elems = h->exterior;
+          if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
+          if ((rc = exchange_begin_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+          ga.elems = h->interior;
+          if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
+          if ((rc = exchange_end_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+        }
+        a.elems = h->exterior;
+        if ((rc = launch_tendency<R>(h, a, h->nexterior, st))) return rc;
+        if ((rc = exchange_begin_t<R>(h, nxt, h->d.nstate, st))) return rc;
+        a.elems = h->interior;
+        if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
+        if ((rc = exchange_end_t<R>(h, nxt, h->d.nstate, st))) return rc;
+      }
+      R *tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+  }
+  if (cur != (R *)Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
+  // the reference leaves dQ scaled by RKA[1] after the last stage (:130-141)
+  const size_t n = (size_t)nreal * h->d.nstate * h->Np;
+  if (rka[0] == 0.0) {
+    CU(cudaMemsetAsync(dQ, 0, n * sizeof(R), st));
+  } else if (n) {
+    scale_kernel<R><<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+        (R *)dQ, (R)rka[0], n);
+    h->launches++;
+  }
+  if (h->timing) {
+    CU(cudaStreamSynchronize(st));
+    double ms = 0;
+    for (size_t i = 0; i + 1 < h->tev_used; i += 2) {
+      float x = 0;
+      cudaEventElapsedTime(&x, h->tev[i], h->tev[i + 1]);
+      ms += x;
+    }
+    h->last_ms = ms;
+    h->last_nl = (int64_t)(h->tev_used / 2);
+  }
+  return 0;
+}
+
+// Derive the per-face neighbour descriptor from vmap+ / elemtobndy and verify that every
+// face follows the conforming tensor-product pattern of Grids.jl:559-637 (orientation 1 or 3).
+int build_conn(cmdg_handle h, const int64_t *vmapM_dev, const int64_t *vmapP_dev,
+               const int64_t *elemtobndy_dev) {
+  const int NQ = h->Nq, NP = h->Np, NFP = h->Nfp;
+  const int64_t nreal = h->d.nrealelem, nelem = h->d.nelem;
+  std::vector<int64_t> vP((size_t)nreal * 6 * NFP), vM((size_t)nreal * 6 * NFP), bnd((size_t)nreal * 6);
+  CU(cudaMemcpy(vP.data(), vmapP_dev, vP.size() * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(vM.data(), vmapM_dev, vM.size() * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(bnd.data(), elemtobndy_dev, bnd.size() * 8, cudaMemcpyDeviceToHost));
+  auto f2v = [NQ](int f, int a, int b) {
+    switch (f) {
+      case 0: return NQ * (a + NQ * b);
+      case 1: return (NQ - 1) + NQ * (a + NQ * b);
+      case 2: return a + NQ * NQ * b;
+      case 3: return a + NQ * ((NQ - 1) + NQ * b);
+      case 4: return a + NQ * b;
+      default: return a + NQ * (b + NQ * (NQ - 1));
+    }
+  };
+  std::vector<int2> conn((size_t)nreal * 6);
+  for (int64_t e = 0; e < nreal; ++e)
+    for (int f = 0; f < 6; ++f) {
+      const int64_t *pm = &vM[((size_t)e * 6 + f) * NFP];
+      const int64_t *pp = &vP[((size_t)e * 6 + f) * NFP];
+      for (int n = 0; n < NFP; ++n)
+        if (pm[n] != (int64_t)NP * e + f2v(f, n % NQ, n / NQ) + 1)
+          return fail(h, CMDG_ERR_UNSUPPORTED, "vmap- does not follow the Grids.jl face-mask order");
+      const int64_t tag = bnd[(size_t)e * 6 + f];
+      if (tag != 0) {
+        if (tag < 0 || tag > h->d.nbc)
+          return fail(h, CMDG_ERR_INVALID, "elemtobndy tag outside 1..nbc (BoundsError(bcs, bctag))");
+        conn[(size_t)e * 6 + f] = make_int2((int)e, conn_meta(f, 0, (int)tag));
+        continue;
+      }
+      const int64_t ep = (pp[0] - 1) / NP;
+      if (ep < 0 || ep >= nelem) return fail(h, CMDG_ERR_INVALID, "vmap+ points outside the state array");
+      int found = -1;
+      for (int fp = 0; fp < 6 && found < 0; ++fp)
+        for (int flip = 0; flip < 2 && found < 0; ++flip) {
+          bool ok = true;
+          for (int n = 0; n < NFP && ok; ++n) {
+            const int a = flip ? NQ - 1 - n % NQ : n % NQ;
+            ok = pp[n] == (int64_t)NP * ep + f2v(fp, a, n / NQ) + 1;
+          }
+          if (ok) found = fp | (flip << 3);
+        }
+      if (found < 0)
+        return fail(h, CMDG_ERR_UNSUPPORTED,
+                    "vmap+ face is not a conforming tensor-product face (orientation 1 or 3)");
+      conn[(size_t)e * 6 + f] = make_int2((int)ep, found);
+    }
+  CU(cudaMalloc(&h->conn, conn.size() * sizeof(int2) + 16));
+  CU(cudaMemcpy(h->conn, conn.data(), conn.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int to_zero_based_list(cmdg_handle h, const int64_t *dev, int64_t n, int **out) {
+  *out = nullptr;
+  if (n <= 0) return 0;
+  std::vector<int64_t> tmp(n);
+  CU(cudaMemcpy(tmp.data(), dev, n * 8, cudaMemcpyDeviceToHost));
+  std::vector<int> v(n);
+  for (int64_t i = 0; i < n; ++i) v[i] = (int)(tmp[i] - 1);
+  CU(cudaMalloc(out, n * sizeof(int)));
+  CU(cudaMemcpy(*out, v.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int to_zero_based_map(cmdg_handle h, const int64_t *dev, int64_t n, int64_t **out) {
+  *out = nullptr;
+  if (n <= 0) return 0;
+  std::vector<int64_t> tmp(n);
+  CU(cudaMemcpy(tmp.data(), dev, n * 8, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) tmp[i] -= 1;
+  CU(cudaMalloc(out, n * 8));
+  CU(cudaMemcpy(*out, tmp.data(), n * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <class R>
+int bind_grid_t(cmdg_handle h, const void *vgeo, const void *sgeo, const void *D) {
+  const int64_t nreal = h->d.nrealelem;
+  const int NP = h->Np, NFP = h->Nfp, NQ = h->Nq;
+  CU(cudaMalloc(&h->vgeoP, (size_t)nreal * 10 * NP * sizeof(R) + 16));
+  CU(cudaMalloc(&h->sgeoP, (size_t)nreal * 6 * 4 * NFP * sizeof(R) + 16));
+  if (nreal > 0) {
+    const size_t nv = (size_t)nreal * NP, ns = (size_t)nreal * 6 * NFP;
+    pack_vgeo_kernel<R><<<(unsigned)((nv + 255) / 256), 256>>>((R *)h->vgeoP, (const R *)vgeo, NP, 25, nreal);
+    pack_sgeo_kernel<R><<<(unsigned)((ns + 255) / 256), 256>>>((R *)h->sgeoP, (const R *)sgeo, NFP, nreal);
+    CU(cudaGetLastError());
+    h->launches += 2;
+  }
+  // D arrives in Julia (column-major) order; keep a row-major copy D[a][b] = D_julia[a, b]
+  std::vector<R> Dj(NQ * NQ), Dr(NQ * NQ);
+  CU(cudaMemcpy(Dj.data(), D, Dj.size() * sizeof(R), cudaMemcpyDeviceToHost));
+  for (int a = 0; a < NQ; ++a)
+    for (int b = 0; b < NQ; ++b) Dr[a * NQ + b] = Dj[a + NQ * b];
+  CU(cudaMalloc(&h->Ddev, Dr.size() * sizeof(R)));
+  CU(cudaMemcpy(h->Ddev, Dr.data(), Dr.size() * sizeof(R), cudaMemcpyHostToDevice));
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+#define DISPATCH_FT(h, expr64, expr32) ((h)->d.float_bytes == CMDG_F64 ? (expr64) : (expr32))
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int cmdg_version(void) { return CMDG_VERSION; }
+
+const char *cmdg_last_error(cmdg_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
+  cmdg_handle h = nullptr;
+  if (!d || !out) return fail(nullptr, CMDG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->struct_bytes != (int32_t)sizeof(cmdg_desc))
+    return fail(nullptr, CMDG_ERR_INVALID, "cmdg_desc size mismatch (ABI)");
+  if (d->float_bytes != CMDG_F64 && d->float_bytes != CMDG_F32)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "float type must be Float64 or Float32");
+  if (d->dim != 3) return fail(nullptr, CMDG_ERR_UNSUPPORTED, "only dim = 3 is supported");
+  if (d->N != 4)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "only polynomial order N = 4 is compiled in");
+  if (d->model != CMDG_MODEL_ATMOS_DRY)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED,
+                "unsupported balance law (only the dry AtmosModel is compiled in)");
+  if (d->nf_first < CMDG_NF_RUSANOV || d->nf_first > CMDG_NF_ROE)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported first-order numerical flux");
+  if (d->nf_second != CMDG_NF_CENTRAL || d->nf_gradient != CMDG_NF_CENTRAL)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "second-order / gradient fluxes must be Central");
+  if (d->orientation < 0 || d->orientation > CMDG_ORIENT_SPHERICAL ||
+      d->ref_state < 0 || d->ref_state > CMDG_REF_HYDROSTATIC ||
+      d->turbulence < 0 || d->turbulence > CMDG_TURB_SMAGORINSKY)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported orientation / reference state / turbulence model");
+  if (d->sources & ~(CMDG_SRC_GRAVITY | CMDG_SRC_CORIOLIS))
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported source term");
+  if ((d->sources & CMDG_SRC_GRAVITY) && d->orientation == CMDG_ORIENT_NONE)
+    return fail(nullptr, CMDG_ERR_INVALID, "Gravity needs an orientation");
+  if (d->ref_state == CMDG_REF_HYDROSTATIC && d->orientation == CMDG_ORIENT_NONE)
+    return fail(nullptr, CMDG_ERR_INVALID, "HydrostaticState needs an orientation");
+  if (d->turbulence == CMDG_TURB_SMAGORINSKY && d->orientation == CMDG_ORIENT_NONE)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "SmagorinskyLilly needs an orientation");
+  if (d->nbc < 0 || d->nbc > 6) return fail(nullptr, CMDG_ERR_INVALID, "nbc must be 0..6");
+  for (int i = 0; i < d->nbc; ++i)
+    if (d->bc_kind[i] != CMDG_BC_FREESLIP && d->bc_kind[i] != CMDG_BC_NOSLIP)
+      return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported boundary condition");
+  if (d->nstate != 5) return fail(nullptr, CMDG_ERR_UNSUPPORTED, "dry AtmosModel has 5 prognostic states (tracers/moisture unsupported)");
+  if (d->naux != expected_naux(*d))
+    return fail(nullptr, CMDG_ERR_INVALID, "naux does not match the model's auxiliary state");
+  const int gf = d->turbulence == CMDG_TURB_SMAGORINSKY ? 10 : 9;
+  if (d->ngradflux != gf || d->ngrad != (gf == 10 ? 5 : 4))
+    return fail(nullptr, CMDG_ERR_INVALID, "ngrad/ngradflux do not match the model");
+  if (d->nrealelem < 0 || d->nelem < d->nrealelem || d->nelem > 0x7fffffffLL)
+    return fail(nullptr, CMDG_ERR_INVALID, "bad element counts");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, CMDG_ERR_NODEVICE, "no CUDA device available (libcmdg has no CPU fallback)");
+  h = new cmdg_handle_s();
+  h->d = *d;
+  h->Nq = d->N + 1;
+  h->Np = h->Nq * h->Nq * h->Nq;
+  h->Nfp = h->Nq * h->Nq;
+  h->fb = d->float_bytes;
+  h->aux_model = d->orientation != CMDG_ORIENT_NONE || d->ref_state != CMDG_REF_NONE;
+  const bool zero_visc = d->turbulence != CMDG_TURB_SMAGORINSKY && d->turb_param == 0.0;
+  h->visc = !(d->skip_zero_viscosity && zero_visc);
+  cudaError_t e1 = cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+  cudaError_t e2 = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
+  cudaError_t e3 = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
+  }
+  *out = h;
+  return CMDG_OK;
+}
+
+int cmdg_destroy(cmdg_handle h) {
+  if (!h) return CMDG_OK;
+  cudaDeviceSynchronize();
+  void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
+                  h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev};
+  for (void *p : bufs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  delete h;
+  return CMDG_OK;
+}
+
+int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int64_t *vmapM,
+                   const int64_t *vmapP, const int64_t *elemtobndy, const void *D,
+                   const int64_t *interiorelems, int64_t ninterior,
+                   const int64_t *exteriorelems, int64_t nexterior, const int64_t *vmapsend,
+                   int64_t nvmapsend, const int64_t *vmaprecv, int64_t nvmaprecv,
+                   const int32_t *nabrtorank, const int64_t *nabrtovmapsend,
+                   const int64_t *nabrtovmaprecv, int32_t nnabr) {
+  if (!h) return CMDG_ERR_INVALID;
+  if (h->grid_bound) return fail(h, CMDG_ERR_INVALID, "grid already bound");
+  if (!vgeo || !sgeo || !vmapM || !vmapP || !elemtobndy || !D)
+    return fail(h, CMDG_ERR_INVALID, "null grid array");
+  if (ninterior + nexterior != h->d.nrealelem)
+    return fail(h, CMDG_ERR_INVALID, "interiorelems + exteriorelems must cover the real elements");
+  int rc = DISPATCH_FT(h, bind_grid_t<double>(h, vgeo, sgeo, D), bind_grid_t<float>(h, vgeo, sgeo, D));
+  if (rc) return rc;
+  if ((rc = build_conn(h, vmapM, vmapP, elemtobndy))) return rc;
+  if ((rc = to_zero_based_list(h, interiorelems, ninterior, &h->interior))) return rc;
+  if ((rc = to_zero_based_list(h, exteriorelems, nexterior, &h->exterior))) return rc;
+  h->ninterior = ninterior;
+  h->nexterior = nexterior;
+  if ((rc = to_zero_based_map(h, vmapsend, nvmapsend, &h->vmapsend0))) return rc;
+  if ((rc = to_zero_based_map(h, vmaprecv, nvmaprecv, &h->vmaprecv0))) return rc;
+  h->nvmapsend = nvmapsend;
+  h->nvmaprecv = nvmaprecv;
+  h->nabrtorank.assign(nabrtorank, nabrtorank + (nnabr > 0 ? nnabr : 0));
+  for (int n = 0; n < nnabr; ++n) {
+    h->sendrange.push_back(nabrtovmapsend[2 * n] - 1);
+    h->sendrange.push_back(nabrtovmapsend[2 * n + 1]);
+    h->recvrange.push_back(nabrtovmaprecv[2 * n] - 1);
+    h->recvrange.push_back(nabrtovmaprecv[2 * n + 1]);
+  }
+  h->grid_bound = true;
+  return CMDG_OK;
+}
+
+int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
+  if (!h) return CMDG_ERR_INVALID;
+  if (!aux) return fail(h, CMDG_ERR_INVALID, "state_auxiliary is null");
+  if (h->visc && !gradflux)
+    return fail(h, CMDG_ERR_INVALID, "state_gradient_flux is required unless skip_zero_viscosity applies");
+  h->aux = aux;
+  h->gradflux = gradflux;
+  return CMDG_OK;
+}
+
+static int check_ready(cmdg_handle h) {
+  if (!h) return CMDG_ERR_INVALID;
+  if (!h->grid_bound || !h->aux) return fail(h, CMDG_ERR_INVALID, "bind the grid and the state first");
+  return 0;
+}
+
+int cmdg_tendency(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double beta,
+                  cmdg_stream stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!dQ || !Q) return fail(h, CMDG_ERR_INVALID, "null state array");
+  cudaStream_t st = (cudaStream_t)stream;
+  return DISPATCH_FT(h, tendency_t<double>(h, dQ, Q, t, alpha, beta, st),
+                     tendency_t<float>(h, dQ, Q, t, alpha, beta, st));
+}
+
+int cmdg_lsrk_update(cmdg_handle h, void *dQ, void *Q, double rka, double rkb, double dt,
+                     cmdg_stream stream) {
+  if (!h) return CMDG_ERR_INVALID;
+  if (!dQ || !Q) return fail(h, CMDG_ERR_INVALID, "null state array");
+  cudaStream_t st = (cudaStream_t)stream;
+  return DISPATCH_FT(h, lsrk_update_t<double>(h, dQ, Q, rka, rkb, dt, st),
+                     lsrk_update_t<float>(h, dQ, Q, rka, rkb, dt, st));
+}
+
+int cmdg_lsrk_steps(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int32_t nstage,
+                    const double *rka, const double *rkb, const double *rkc, int64_t nsteps,
+                    cmdg_stream stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!dQ || !Q || !rka || !rkb || !rkc || nstage <= 0 || nsteps < 0)
+    return fail(h, CMDG_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return DISPATCH_FT(h, lsrk_steps_t<double>(h, Q, dQ, t0, dt, nstage, rka, rkb, rkc, nsteps, st),
+                     lsrk_steps_t<float>(h, Q, dQ, t0, dt, nstage, rka, rkb, rkc, nsteps, st));
+}
+
+int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int32_t nstage,
+                         const double *rka, const double *rkb, const double *rkc,
+                         int64_t nsteps) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!Q_host) return fail(h, CMDG_ERR_INVALID, "null host state");
+  const size_t all = (size_t)h->d.nelem * h->d.nstate * h->Np * h->fb;
+  const size_t real = (size_t)h->d.nrealelem * h->d.nstate * h->Np * h->fb;
+  if (!h->Qdev) {
+    CU(cudaMalloc(&h->Qdev, all));
+    CU(cudaMalloc(&h->dQdev, all));
+    CU(cudaMemset(h->Qdev, 0, all));
+    CU(cudaMemset(h->dQdev, 0, all));
+  }
+  CU(cudaMemcpyAsync(h->Qdev, Q_host, real, cudaMemcpyHostToDevice, 0));
+  rc = cmdg_lsrk_steps(h, h->Qdev, h->dQdev, t0, dt, nstage, rka, rkb, rkc, nsteps, nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(Q_host, h->Qdev, real, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  return CMDG_OK;
+}
+
+int cmdg_comm_unique_id(void *id128) {
+  std::string err;
+  if (!id128) return CMDG_ERR_INVALID;
+  if (!g_nccl.load(err)) return fail(nullptr, CMDG_ERR_NCCL, err);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, CMDG_ERR_NCCL, g_nccl.GetErrorString(r));
+  memcpy(id128, &id, 128);
+  return CMDG_OK;
+}
+
+int cmdg_comm_init(cmdg_handle h, const void *id128, int32_t rank, int32_t nranks) {
+  if (!h || !id128) return CMDG_ERR_INVALID;
+  std::string err;
+  if (!g_nccl.load(err)) return fail(h, CMDG_ERR_NCCL, err);
+  if (h->comm) return fail(h, CMDG_ERR_INVALID, "communicator already initialised");
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  h->rank = rank;
+  h->nranks = nranks;
+  return CMDG_OK;
+}
+
+int cmdg_exchange_begin(cmdg_handle h, void *array, int32_t nstate, cmdg_stream stream) {
+  if (!h || !array) return CMDG_ERR_INVALID;
+  if (!h->grid_bound) return fail(h, CMDG_ERR_INVALID, "bind the grid first");
+  cudaStream_t st = (cudaStream_t)stream;
+  return DISPATCH_FT(h, exchange_begin_t<double>(h, array, nstate, st),
+                     exchange_begin_t<float>(h, array, nstate, st));
+}
+
+int cmdg_exchange_end(cmdg_handle h, void *array, int32_t nstate, cmdg_stream stream) {
+  if (!h || !array) return CMDG_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  return DISPATCH_FT(h, exchange_end_t<double>(h, array, nstate, st),
+                     exchange_end_t<float>(h, array, nstate, st));
+}
+
+int cmdg_sync(cmdg_handle h) {
+  if (!h) return CMDG_ERR_INVALID;
+  CU(cudaStreamSynchronize(h->comm_stream));
+  CU(cudaDeviceSynchronize());
+  return CMDG_OK;
+}
+
+int64_t cmdg_kernel_launches(cmdg_handle h) { return h ? h->launches : -1; }
+
+int cmdg_set_timing(cmdg_handle h, int32_t enable) {
+  if (!h) return CMDG_ERR_INVALID;
+  h->timing = enable != 0;
+  h->last_ms = -1;
+  h->last_nl = 0;
+  return CMDG_OK;
+}
+
+double cmdg_last_kernel_ms(cmdg_handle h, int64_t *nl) {
+  if (!h) return -1;
+  if (nl) *nl = h->last_nl;
+  return h->last_ms;
+}
+
+}  // extern "C"

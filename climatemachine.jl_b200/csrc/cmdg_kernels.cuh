@@ -1,0 +1,843 @@
+// cmdg_kernels.cuh -- sm_100a device code of libcmdg.
+//
+// One thread block owns one element (Np = Nq^3 nodes, one thread per node).  A tendency
+// evaluation is ONE kernel: volume term, all six face terms, sources, the alpha/beta
+// combination with the old tendency and (optionally) the low-storage RK stage update are
+// fused, so every array word is touched once per stage:
+//
+//   reference (src/Numerics/DGMethods/DGModel_kernels.jl)          here
+//   volume_tendency! H  (:64-309)   \
+//   volume_tendency! V  (:312-548)   |
+//   dgsem_interface_tendency! x4     |--> dg_tendency_kernel
+//       (:588-901)                   |
+//   kernel_nodal_update_auxiliary_state! (:1769-1825)
+//   update! (ODESolvers/LowStorageRungeKuttaMethod.jl:146-158)  /
+//
+// Memory-system design (the path is HBM-bound, ~1.3 flop/B in FP64):
+//   * state, tendency and geometry are read with fully coalesced 8-byte loads, one
+//     contiguous Np-run per (state, element) -- the Np x nstate x nelem layout of
+//     MPIStateArray makes every column of an element a 1000-byte contiguous run;
+//   * geometry comes from a private packed copy (10 of the 25 vgeo columns with the mass
+//     matrix folded into the metric terms, 4 of 5 sgeo rows with vMI*sM folded), built
+//     once in cmdg_bind_grid;
+//   * the 25 x 6 Int64 vmap+ entries per element are replaced by one 8-byte descriptor
+//     per face (neighbour element, neighbour face, orientation, boundary tag);
+//   * contravariant fluxes are staged in shared memory and contracted with the Nq x Nq
+//     derivative matrix held in shared memory; neighbour traces are gathered once per face
+//     node into shared memory at kernel start so their latency overlaps the volume work.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmdg {
+
+enum { NF_RUSANOV = 0, NF_CENTRAL = 1, NF_ROE = 2 };
+enum { TURB_CONST_KINEMATIC = 0, TURB_CONST_DYNAMIC = 1, TURB_SMAGORINSKY = 2 };
+enum { SRC_GRAVITY = 1, SRC_CORIOLIS = 2 };
+enum { BC_FREESLIP = 1, BC_NOSLIP = 2 };
+
+// Uniform (per launch) physics parameters of the dry AtmosModel.
+template <class R>
+struct AtmosParams {
+  R R_d, cp_d, cv_d, T_0, MSLP, grav, two_Omega, inv_Pr_turb;
+  R gamma;       // cp_d / cv_d
+  R inv_cv;      // 1 / cv_d
+  R kappa;       // R_d / cp_d
+  R turb_param;  // nu, rho*nu or C_smag
+  int turbulence, with_divergence;
+  int sources;
+  int subtract_off;
+  int horizontal_diffusion;
+  int bc_kind[6];
+  // auxiliary-state column ids (0-based), -1 when absent
+  int a_Phi, a_gradPhi, a_ref_rho, a_ref_p, a_Delta, a_theta_v, a_T;
+  int naux, ngradflux;
+};
+
+template <class R>
+struct TendArgs {
+  const R *Q;          // [nelem][5][Np]
+  const R *aux;        // [nelem][naux][Np]
+  const R *gradflux;   // [nelem][ngradflux][Np]
+  R *dQ;               // [nelem][5][Np]
+  R *Qout;             // fused RK update target (may alias nothing in Q); NULL = no update
+  R *aux_out;          // write theta_v / air_T here (NULL = don't)
+  const R *vgeoP;      // [nreal][10][Np]  M*xi{m}x{d} (m-major), MI
+  const R *sgeoP;      // [nreal][6][4][Nfp]  n1,n2,n3, sM*vMI
+  const int2 *conn;    // [nreal][6]  x = neighbour element (0-based), y = meta
+  const int *elems;    // launch list (0-based element ids) or NULL for identity
+  const R *D;          // [Nq][Nq] row-major copy of Julia's D (D[a][b] = D_julia[a+1,b+1])
+  R alpha, beta;       // dQ = alpha*RHS + beta*dQ
+  R rkb_dt;            // Qout = Q + rkb_dt * dQ
+  R t;
+};
+
+// conn.y layout: bits 0-2 neighbour face (0..5), bit 3 flip of first face index,
+// bits 4-7 boundary tag (0 = interior face)
+__host__ __device__ inline int conn_meta(int nface, int flip, int bctag) {
+  return nface | (flip << 3) | (bctag << 4);
+}
+
+template <int NQ>
+__device__ __forceinline__ int face_to_vol(int f, int a, int b) {
+  switch (f) {
+    case 0: return NQ * (a + NQ * b);
+    case 1: return (NQ - 1) + NQ * (a + NQ * b);
+    case 2: return a + NQ * NQ * b;
+    case 3: return a + NQ * ((NQ - 1) + NQ * b);
+    case 4: return a + NQ * b;
+    default: return a + NQ * (b + NQ * (NQ - 1));
+  }
+}
+
+template <class R> __device__ __forceinline__ R rsqrt_(R x);
+template <> __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+template <> __device__ __forceinline__ float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+template <class R> __device__ __forceinline__ R sqrt_(R x);
+template <> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+template <class R> __device__ __forceinline__ R pow_(R x, R y);
+template <> __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+template <> __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+template <class R> __device__ __forceinline__ R cbrt_(R x);
+template <> __device__ __forceinline__ double cbrt_(double x) { return cbrt(x); }
+template <> __device__ __forceinline__ float cbrt_(float x) { return cbrtf(x); }
+
+// Dry-air thermodynamic state from the prognostic state
+// (src/Atmos/Model/thermo_states.jl:67-77, moisture.jl:32-46; Thermodynamics.jl PhaseDry).
+template <class R>
+struct Thermo {
+  R rinv, T, p;
+};
+template <class R>
+__device__ __forceinline__ Thermo<R> thermo(const AtmosParams<R> &P, const R q[5], R Phi) {
+  Thermo<R> th;
+  th.rinv = R(1) / q[0];
+  R ke = th.rinv * (q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) * R(0.5);
+  R e_int = th.rinv * (q[4] - ke - q[0] * Phi);
+  th.T = P.T_0 + e_int * P.inv_cv;
+  th.p = P.R_d * q[0] * th.T;
+  return th;
+}
+
+// Normal component of the first-order flux, n.F(q)  (tendencies_{mass,momentum,energy}.jl)
+template <class R>
+__device__ __forceinline__ void normal_flux(const R q[5], R rinv, R pflux, R p, const R n[3],
+                                            R fn[5], R &un) {
+  un = rinv * (q[1] * n[0] + q[2] * n[1] + q[3] * n[2]);
+  fn[0] = q[0] * un;
+  fn[1] = q[1] * un + pflux * n[0];
+  fn[2] = q[2] * un + pflux * n[1];
+  fn[3] = q[3] * un + pflux * n[2];
+  fn[4] = (q[4] + p) * un;
+}
+
+// Second-order (diffusive) flux F2[d][s] of the dry AtmosModel
+// (tendencies_momentum.jl:36-43, tendencies_energy.jl:27-59, TurbulenceClosures.jl:364-499).
+// gf: grad h_tot[3], S11,S21,S31,S22,S32,S33, [N2]
+template <class R>
+__device__ __forceinline__ void flux_second_order(const AtmosParams<R> &P, const R q[5],
+                                                  const R *gf, const R gradPhi[3], R Delta,
+                                                  R F2[3][5]) {
+  const R S[3][3] = {{gf[3], gf[4], gf[5]}, {gf[4], gf[6], gf[7]}, {gf[5], gf[7], gf[8]}};
+  R nu[3];
+  if (P.turbulence == TURB_SMAGORINSKY) {
+    R norm2 = S[0][0] * S[0][0] + 2 * S[1][0] * S[1][0] + 2 * S[2][0] * S[2][0] +
+              S[1][1] * S[1][1] + 2 * S[2][1] * S[2][1] + S[2][2] * S[2][2];
+    R normS = sqrt_<R>(2 * norm2);
+    R k[3] = {gradPhi[0] / P.grav, gradPhi[1] / P.grav, gradPhi[2] / P.grav};
+    // eps(normS): spacing of floating point numbers at normS
+    R epsn;
+    if (sizeof(R) == 8) {
+      double x = fabs((double)normS);
+      epsn = (R)(x == 0.0 ? 4.9406564584124654e-324 : (nextafter(x, 1.0e308 * 10) - x));
+    } else {
+      float x = fabsf((float)normS);
+      epsn = (R)(x == 0.0f ? 1.4012984643e-45f : (nextafterf(x, 3.0e38f * 10) - x));
+    }
+    R Ri = gf[9] / (normS * normS + epsn);
+    R fb = R(1) - Ri * P.inv_Pr_turb;
+    fb = fb < R(0) ? R(0) : (fb > R(1) ? R(1) : fb);
+    R f_b2 = sqrt_<R>(fb);
+    R Cd = P.turb_param * Delta;
+    R nu0 = normS * (Cd * Cd) + R(1e-5);
+    R dotnuk = nu0 * k[0] + nu0 * k[1] + nu0 * k[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      R nu_v = k[i] * dotnuk;
+      nu[i] = (nu0 - nu_v) + nu_v * f_b2;
+    }
+  } else {
+    R nuc = (P.turbulence == TURB_CONST_KINEMATIC) ? P.turb_param : P.turb_param / q[0];
+    nu[0] = nu[1] = nu[2] = nuc;
+  }
+  R trS = S[0][0] + S[1][1] + S[2][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    R tau[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tau[j] = (-2 * nu[i]) * S[i][j];
+    if (P.turbulence != TURB_SMAGORINSKY && P.with_divergence) tau[i] += (2 * nu[i] / 3) * trS;
+    F2[i][0] = R(0);
+    F2[i][1] = tau[0] * q[0];
+    F2[i][2] = tau[1] * q[0];
+    F2[i][3] = tau[2] * q[0];
+    R D_t = nu[i] * P.inv_Pr_turb;
+    F2[i][4] = (tau[0] * q[1] + tau[1] * q[2] + tau[2] * q[3]) + ((-D_t) * gf[i]) * q[0];
+  }
+}
+
+// Roe dissipation for the dry model (src/Atmos/Model/AtmosModel.jl:967-1062).
+template <class R>
+__device__ __forceinline__ void roe_dissipation(const AtmosParams<R> &P, const R n[3],
+                                                const R qm[5], const Thermo<R> &tm,
+                                                const R qp[5], const Thermo<R> &tp, R Phi,
+                                                R diss[5]) {
+  R um[3] = {qm[1] * tm.rinv, qm[2] * tm.rinv, qm[3] * tm.rinv};
+  R up[3] = {qp[1] * tp.rinv, qp[2] * tp.rinv, qp[3] * tp.rinv};
+  R hm = qm[4] * tm.rinv + P.R_d * tm.T;
+  R hp = qp[4] * tp.rinv + P.R_d * tp.T;
+  R c2m = P.gamma * P.R_d * tm.T, c2p = P.gamma * P.R_d * tp.T;
+  R srm = sqrt_<R>(qm[0]), srp = sqrt_<R>(qp[0]);
+  R iw = R(1) / (srm + srp);
+  R rt = sqrt_<R>(qm[0] * qp[0]);
+  R ut[3] = {(srm * um[0] + srp * up[0]) * iw, (srm * um[1] + srp * up[1]) * iw,
+             (srm * um[2] + srp * up[2]) * iw};
+  R ht = (srm * hm + srp * hp) * iw;
+  R ct2 = (srm * c2m + srp * c2p) * iw;
+  R ct = sqrt_<R>(ct2);
+  R utn = ut[0] * n[0] + ut[1] * n[1] + ut[2] * n[2];
+  R drho = qp[0] - qm[0];
+  R dp = tp.p - tm.p;
+  R du[3] = {up[0] - um[0], up[1] - um[1], up[2] - um[2]};
+  R dun = du[0] * n[0] + du[1] * n[1] + du[2] * n[2];
+  R w1 = fabs(utn - ct) * (dp - rt * ct * dun) / (2 * ct2);
+  R w2 = fabs(utn + ct) * (dp + rt * ct * dun) / (2 * ct2);
+  R w3 = fabs(utn) * (drho - dp / ct2);
+  R w4 = fabs(utn) * rt;
+  diss[0] = (w1 + w2 + w3) * R(0.5);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    diss[1 + c] = (w1 * (ut[c] - ct * n[c]) + w2 * (ut[c] + ct * n[c]) + w3 * ut[c] +
+                   w4 * (du[c] - dun * n[c])) * R(0.5);
+  R utut = ut[0] * ut[0] + ut[1] * ut[1] + ut[2] * ut[2];
+  R utdu = ut[0] * du[0] + ut[1] * du[1] + ut[2] * du[2];
+  diss[4] = (w1 * (ht - ct * utn) + w2 * (ht + ct * utn) +
+             w3 * (utut * R(0.5) + Phi - P.T_0 * P.cv_d) + w4 * (utdu - utn * dun)) * R(0.5);
+}
+
+template <int NQ>
+struct Dims {
+  static constexpr int NP = NQ * NQ * NQ;
+  static constexpr int NFP = NQ * NQ;
+  static constexpr int NFN = 6 * NFP;
+  static constexpr int BLOCK = ((NP + 31) / 32) * 32;
+};
+
+// ---------------------------------------------------------------------------------------
+// Fused DG tendency (+ optional RK stage update).  Template switches select the code that
+// is compiled in: NF1 numerical flux, AUX = model has orientation/reference-state columns,
+// VISC = second-order fluxes from the gradient-flux array are included.
+// ---------------------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+template <class R, int NQ, bool AUX, bool VISC>
+struct TendSmem {
+  static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
+  R Q[5][NP];                              // own state
+  R F[3][5][NP];                           // contravariant fluxes  M xi_m . F
+  R Qp[5][NFN];                            // neighbour traces; reused for the face results
+  R P[NP], Rinv[NP];                       // own pressure, 1/rho
+  R Phi[AUX ? NP : 1], Pref[AUX ? NP : 1]; // own geopotential, reference pressure
+  R Ap[2][AUX ? NFN : 1];                  // neighbour geopotential, reference pressure
+  R GF[VISC ? 10 : 1][VISC ? NP : 1];      // own gradient flux
+  R GFp[VISC ? 10 : 1][VISC ? NFN : 1];    // neighbour gradient flux
+  R D[NQ * NQ];
+};
+
+template <class R, int NQ, int NF1, bool AUX, bool VISC>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
+dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
+  constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
+  constexpr int BLOCK = Dims<NQ>::BLOCK;
+  constexpr int NGF = 10;  // max gradient-flux columns
+  constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TendSmem<R, NQ, AUX, VISC> &S = *reinterpret_cast<TendSmem<R, NQ, AUX, VISC> *>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const size_t eoffQ = (size_t)e * 5 * NP;
+  const size_t eoffA = (size_t)e * P.naux * NP;
+  const R *__restrict__ Qg = A.Q;
+  const R *__restrict__ auxg = A.aux;
+
+  // ---- (a) face descriptors of my face items ----
+  int2 cn[NITEM];
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    cn[r] = (it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
+  }
+  if (tid < NQ * NQ) S.D[tid] = A.D[tid];
+
+  // ---- (b) issue my node's loads ----
+  R MI = 0;
+  R dQold[5] = {0, 0, 0, 0, 0};
+  R q[5] = {1, 0, 0, 0, 0};
+  R g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  R Phi = 0, pref = 0, rref = 0, Delta = 0;
+  R gPhi[3] = {0, 0, 0};
+  R gf[NGF];
+  if (tid < NP) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) q[s] = Qg[eoffQ + (size_t)s * NP + tid];
+    if (AUX) {
+      if (P.a_Phi >= 0) Phi = auxg[eoffA + (size_t)P.a_Phi * NP + tid];
+      if (P.a_ref_p >= 0) pref = auxg[eoffA + (size_t)P.a_ref_p * NP + tid];
+      if ((P.sources & SRC_GRAVITY) && P.subtract_off)
+        rref = auxg[eoffA + (size_t)P.a_ref_rho * NP + tid];
+      if (P.a_gradPhi >= 0 && (VISC || (P.sources & SRC_GRAVITY))) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gPhi[d] = auxg[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
+      }
+    }
+    if (VISC) {
+      const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+#pragma unroll
+      for (int s = 0; s < NGF; ++s)
+        gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
+      if (AUX && P.a_Delta >= 0) Delta = auxg[eoffA + (size_t)P.a_Delta * NP + tid];
+    }
+    const R *__restrict__ vg = A.vgeoP + (size_t)e * 10 * NP + tid;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) g[c] = vg[(size_t)c * NP];
+    MI = vg[(size_t)9 * NP];
+    if (A.beta != R(0)) {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) dQold[s] = A.dQ[eoffQ + (size_t)s * NP + tid];
+    }
+  }
+
+  // ---- (c) asynchronous gathers of the neighbour traces into shared memory ----
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    if (it < NFN && ((cn[r].y >> 4) & 15) == 0) {
+      const int fn = it % NFP;
+      int a = fn % NQ;
+      const int b = fn / NQ;
+      if (cn[r].y & 8) a = NQ - 1 - a;
+      const int vp = face_to_vol<NQ>(cn[r].y & 7, a, b);
+      const size_t offp = (size_t)cn[r].x * 5 * NP + vp;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&S.Qp[s][it], Qg + offp + (size_t)s * NP);
+      if (AUX) {
+        const size_t offa = (size_t)cn[r].x * P.naux * NP + vp;
+        if (P.a_Phi >= 0) cp_async<sizeof(R)>(&S.Ap[0][it], auxg + offa + (size_t)P.a_Phi * NP);
+        if (P.a_ref_p >= 0)
+          cp_async<sizeof(R)>(&S.Ap[1][AUX ? it : 0], auxg + offa + (size_t)P.a_ref_p * NP);
+      }
+      if (VISC) {
+        const size_t offg = (size_t)cn[r].x * P.ngradflux * NP + vp;
+        for (int s = 0; s < P.ngradflux; ++s)
+          cp_async<sizeof(R)>(&S.GFp[VISC ? s : 0][VISC ? it : 0],
+                              A.gradflux + offg + (size_t)s * NP);
+      }
+    }
+  }
+
+  // ---- (d) volume: fluxes at my node ----
+  R src[5] = {0, 0, 0, 0, 0};
+  if (tid < NP) {
+    const Thermo<R> th = thermo<R>(P, q, Phi);
+    const R pflux = (AUX && P.subtract_off) ? th.p - pref : th.p;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) S.Q[s][tid] = q[s];
+    S.P[tid] = th.p;
+    S.Rinv[tid] = th.rinv;
+    if (AUX) {
+      S.Phi[tid] = Phi;
+      S.Pref[tid] = pref;
+    }
+    if (A.aux_out) {
+      // kernel_nodal_update_auxiliary_state! / DryModel (moisture.jl:58-69)
+      A.aux_out[eoffA + (size_t)P.a_theta_v * NP + tid] = th.T / pow_<R>(th.p / P.MSLP, P.kappa);
+      A.aux_out[eoffA + (size_t)P.a_T * NP + tid] = th.T;
+    }
+    const R u[3] = {q[1] * th.rinv, q[2] * th.rinv, q[3] * th.rinv};
+    R F[3][5];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      F[d][0] = q[1 + d];
+      F[d][1] = q[1 + d] * u[0];
+      F[d][2] = q[1 + d] * u[1];
+      F[d][3] = q[1 + d] * u[2];
+      F[d][1 + d] += pflux;
+      F[d][4] = u[d] * (q[4] + th.p);
+    }
+    if (VISC) {
+#pragma unroll
+      for (int s = 0; s < NGF; ++s) S.GF[VISC ? s : 0][VISC ? tid : 0] = gf[s];
+      R F2[3][5];
+      flux_second_order<R>(P, q, gf, gPhi, Delta, F2);
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int s = 0; s < 5; ++s) F[d][s] += F2[d][s];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        S.F[m][s][tid] = g[3 * m] * F[0][s] + g[3 * m + 1] * F[1][s] + g[3 * m + 2] * F[2][s];
+    // sources (tendencies_momentum.jl:66-92); added in the vertical launch in the reference
+    if (AUX && (P.sources & SRC_GRAVITY)) {
+      const R rr = q[0] - rref;
+      src[1] = -rr * gPhi[0];
+      src[2] = -rr * gPhi[1];
+      src[3] = -rr * gPhi[2];
+    }
+    if (P.sources & SRC_CORIOLIS) {
+      src[1] += P.two_Omega * q[2];
+      src[2] -= P.two_Omega * q[1];
+    }
+  }
+  __syncthreads();
+
+  // ---- volume: weak derivative  MI * D^T (M xi . F) ----
+  R acc[5] = {0, 0, 0, 0, 0};
+  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
+  if (tid < NP) {
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const R d1 = S.D[n * NQ + i], d2 = S.D[n * NQ + j], d3 = S.D[n * NQ + k];
+      const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        acc[s] += d1 * S.F[0][s][o1] + d2 * S.F[1][s][o2] + d3 * S.F[2][s][o3];
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) acc[s] = MI * acc[s] + src[s];
+  }
+
+  // ---- faces: numerical flux at every face node of this element ----
+  cp_async_wait_all();
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    if (it >= NFN) break;
+    const int f = it / NFP, fn = it - f * NFP;
+    const int2 c = cn[r];
+    const int bctag = (c.y >> 4) & 15;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    const R *__restrict__ sg = A.sgeoP + ((size_t)e * 6 + f) * 4 * NFP + fn;
+    const R n[3] = {sg[0], sg[NFP], sg[2 * NFP]};
+    const R sMvMI = sg[3 * NFP];
+    R qm[5], qp[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) qm[s] = S.Q[s][vm];
+    Thermo<R> tm;
+    tm.rinv = S.Rinv[vm];
+    tm.p = S.P[vm];
+    tm.T = tm.p * tm.rinv / P.R_d;
+    const R Phim = AUX ? S.Phi[AUX ? vm : 0] : R(0);
+    const R prefm = AUX ? S.Pref[AUX ? vm : 0] : R(0);
+    R Phip = Phim, prefp = prefm;
+    if (bctag == 0) {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) qp[s] = S.Qp[s][it];
+      if (AUX) {
+        if (P.a_Phi >= 0) Phip = S.Ap[0][AUX ? it : 0];
+        if (P.a_ref_p >= 0) prefp = S.Ap[1][AUX ? it : 0];
+      }
+    } else {
+      // boundary_state! (src/Atmos/Model/bc_momentum.jl:24-33, 60-70)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) qp[s] = qm[s];
+      const int kind = P.bc_kind[bctag - 1];
+      if (kind == BC_FREESLIP) {
+        const R run = 2 * (qm[1] * n[0] + qm[2] * n[1] + qm[3] * n[2]);
+        qp[1] -= run * n[0];
+        qp[2] -= run * n[1];
+        qp[3] -= run * n[2];
+      } else {
+        qp[1] = -qm[1];
+        qp[2] = -qm[2];
+        qp[3] = -qm[3];
+      }
+    }
+    const Thermo<R> tp = thermo<R>(P, qp, Phip);
+    R fm[5], fp[5], unm, unp;
+    normal_flux<R>(qm, tm.rinv, (AUX && P.subtract_off) ? tm.p - prefm : tm.p, tm.p, n, fm, unm);
+    normal_flux<R>(qp, tp.rinv, (AUX && P.subtract_off) ? tp.p - prefp : tp.p, tp.p, n, fp, unp);
+    R fl[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) fl[s] = R(0.5) * (fm[s] + fp[s]);
+    if (NF1 == NF_RUSANOV) {
+      const R cm = sqrt_<R>(P.gamma * tm.p * tm.rinv);
+      const R cp = sqrt_<R>(P.gamma * P.R_d * tp.T);
+      const R lam = R(0.5) * fmax(fabs(unm) + cm, fabs(unp) + cp);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) fl[s] += lam * (qm[s] - qp[s]);
+    } else if (NF1 == NF_ROE) {
+      R diss[5];
+      roe_dissipation<R>(P, n, qm, tm, qp, tp, Phim, diss);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) fl[s] -= diss[s];
+    }
+    if (VISC && bctag == 0) {
+      // CentralNumericalFluxSecondOrder (NumericalFluxes.jl:668-715); wall faces carry no
+      // diffusive flux for FreeSlip/NoSlip + Insulating (bc_momentum.jl:44-49, bc_energy.jl:12-17)
+      R gfm[NGF], gfp[NGF];
+#pragma unroll
+      for (int s = 0; s < NGF; ++s) {
+        gfm[s] = S.GF[VISC ? s : 0][VISC ? vm : 0];
+        gfp[s] = (s < P.ngradflux) ? S.GFp[VISC ? s : 0][VISC ? it : 0] : R(0);
+      }
+      R gPm[3] = {0, 0, 0}, gPp[3] = {0, 0, 0}, Dm = 0, Dp = 0;
+      if (P.turbulence == TURB_SMAGORINSKY) {
+        const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
+        const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
+        const size_t om = eoffA + vm, op = (size_t)c.x * P.naux * NP + vp;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          gPm[d] = auxg[om + (size_t)(P.a_gradPhi + d) * NP];
+          gPp[d] = auxg[op + (size_t)(P.a_gradPhi + d) * NP];
+        }
+        Dm = auxg[om + (size_t)P.a_Delta * NP];
+        Dp = auxg[op + (size_t)P.a_Delta * NP];
+      }
+      R F2m[3][5], F2p[3][5];
+      flux_second_order<R>(P, qm, gfm, gPm, Dm, F2m);
+      flux_second_order<R>(P, qp, gfp, gPp, Dp, F2p);
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        fl[s] += R(0.5) * ((F2m[0][s] + F2p[0][s]) * n[0] + (F2m[1][s] + F2p[1][s]) * n[1] +
+                           (F2m[2][s] + F2p[2][s]) * n[2]);
+    }
+    // stash vMI*sM*F* in place of the neighbour trace (same thread wrote/reads this slot)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) S.Qp[s][it] = sMvMI * fl[s];
+  }
+  __syncthreads();
+
+  // ---- combine: tendency[vid-] -= vMI sM F*  in face order 1..6, then alpha/beta, RK ----
+  if (tid < NP) {
+    if (i == 0) {
+      const int it = 0 * NFP + j + NQ * k;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+    if (i == NQ - 1) {
+      const int it = 1 * NFP + j + NQ * k;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+    if (j == 0) {
+      const int it = 2 * NFP + i + NQ * k;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+    if (j == NQ - 1) {
+      const int it = 3 * NFP + i + NQ * k;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+    if (k == 0) {
+      const int it = 4 * NFP + i + NQ * j;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+    if (k == NQ - 1) {
+      const int it = 5 * NFP + i + NQ * j;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const R d = A.alpha * acc[s] + A.beta * dQold[s];
+      A.dQ[eoffQ + (size_t)s * NP + tid] = d;
+      if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gradient pass: volume_gradients! H/V (DGModel_kernels.jl:934-1328) +
+// dgsem_interface_gradients! (:1365-1651) with CentralNumericalFluxGradient
+// (NumericalFluxes.jl:65-123), fused per element.  Writes the gradient-flux array.
+//   G  = (u1,u2,u3,h_tot[,theta_v])          (AtmosModel.jl:622-673)
+//   GF = (grad h_tot, sym(grad u)[, N2])      (AtmosModel.jl:675-744)
+// ---------------------------------------------------------------------------------------
+template <class R>
+struct GradArgs {
+  const R *Q, *aux;
+  R *gradflux;
+  const R *vgeoP, *sgeoP;
+  const int2 *conn;
+  const int *elems;
+  const R *D;
+};
+
+template <class R>
+__device__ __forceinline__ void gradient_argument(const AtmosParams<R> &P, const R q[5], R Phi,
+                                                  R G[5]) {
+  const Thermo<R> th = thermo<R>(P, q, Phi);
+  G[0] = th.rinv * q[1];
+  G[1] = th.rinv * q[2];
+  G[2] = th.rinv * q[3];
+  G[3] = q[4] * th.rinv + P.R_d * th.T;
+  G[4] = th.T / pow_<R>(th.p / P.MSLP, P.kappa);  // aux.moisture.theta_v, refreshed from Q
+}
+
+// gf = linear map of the gradient  dG[d][g]  (TurbulenceClosures.jl:351-362,456-470)
+template <class R>
+__device__ __forceinline__ void gradient_flux(const AtmosParams<R> &P, const R dG[3][5],
+                                              const R gradPhi[3], R theta_v, R gf[10]) {
+  gf[0] = dG[0][3];
+  gf[1] = dG[1][3];
+  gf[2] = dG[2][3];
+  gf[3] = dG[0][0];
+  gf[4] = (dG[1][0] + dG[0][1]) * R(0.5);
+  gf[5] = (dG[2][0] + dG[0][2]) * R(0.5);
+  gf[6] = dG[1][1];
+  gf[7] = (dG[2][1] + dG[1][2]) * R(0.5);
+  gf[8] = dG[2][2];
+  gf[9] = (P.turbulence == TURB_SMAGORINSKY)
+              ? (dG[0][4] * gradPhi[0] + dG[1][4] * gradPhi[1] + dG[2][4] * gradPhi[2]) / theta_v
+              : R(0);
+}
+
+template <class R, int NQ, bool AUX>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
+dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
+  constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
+  constexpr int BLOCK = Dims<NQ>::BLOCK;
+  __shared__ R sG[5][NP];
+  __shared__ R sQ[5][NP];
+  __shared__ R sPhi[AUX ? NP : 1];
+  __shared__ R sFace[10][NFN];
+  __shared__ R sD[NQ * NQ];
+  __shared__ int2 sConn[6];
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const size_t eoffQ = (size_t)e * 5 * NP;
+  const size_t eoffA = (size_t)e * P.naux * NP;
+  if (tid < 6) sConn[tid] = A.conn[(size_t)e * 6 + tid];
+  if (tid < NQ * NQ) sD[tid] = A.D[tid];
+  const int nfaces = P.horizontal_diffusion ? 4 : 6;
+
+  R q[5] = {1, 0, 0, 0, 0}, G[5], Phi = 0, gPhi[3] = {0, 0, 0};
+  if (tid < NP) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) q[s] = A.Q[eoffQ + (size_t)s * NP + tid];
+    if (AUX && P.a_Phi >= 0) Phi = A.aux[eoffA + (size_t)P.a_Phi * NP + tid];
+    if (AUX && P.a_gradPhi >= 0 && P.turbulence == TURB_SMAGORINSKY) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
+    }
+    gradient_argument<R>(P, q, Phi, G);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      sG[s][tid] = G[s];
+      sQ[s][tid] = q[s];
+    }
+    if (AUX) sPhi[tid] = Phi;
+  }
+  __syncthreads();
+
+  // faces: vMI sM gf(n (x) (G* - G-)),  G* = (G+ + G-)/2 or g(boundary_state(Q-))
+  for (int it = tid; it < nfaces * NFP; it += BLOCK) {
+    const int f = it / NFP, fn = it - f * NFP;
+    const int2 c = sConn[f];
+    const int bctag = (c.y >> 4) & 15;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    const R *__restrict__ sg = A.sgeoP + ((size_t)e * 6 + f) * 4 * NFP + fn;
+    const R n[3] = {sg[0], sg[NFP], sg[2 * NFP]};
+    const R sMvMI = sg[3 * NFP];
+    R Gm[5], qm[5], qp[5], Gs[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      Gm[s] = sG[s][vm];
+      qm[s] = sQ[s][vm];
+    }
+    const R Phim = AUX ? sPhi[AUX ? vm : 0] : R(0);
+    R gPm[3] = {0, 0, 0};
+    if (P.turbulence == TURB_SMAGORINSKY) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gPm[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + vm];
+    }
+    if (bctag == 0) {
+      int a = fn % NQ, b = fn / NQ;
+      if (c.y & 8) a = NQ - 1 - a;
+      const int vp = face_to_vol<NQ>(c.y & 7, a, b);
+      const size_t offp = (size_t)c.x * 5 * NP + vp;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) qp[s] = A.Q[offp + (size_t)s * NP];
+      R Phip = 0;
+      if (AUX && P.a_Phi >= 0) Phip = A.aux[(size_t)c.x * P.naux * NP + (size_t)P.a_Phi * NP + vp];
+      gradient_argument<R>(P, qp, Phip, Gs);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) Gs[s] = R(0.5) * (Gs[s] + Gm[s]) - Gm[s];
+    } else {
+      // gradient-flux boundary state (bc_momentum.jl:34-43, 71-80)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) qp[s] = qm[s];
+      const int kind = P.bc_kind[bctag - 1];
+      if (kind == BC_FREESLIP) {
+        const R run = qm[1] * n[0] + qm[2] * n[1] + qm[3] * n[2];
+        qp[1] -= run * n[0];
+        qp[2] -= run * n[1];
+        qp[3] -= run * n[2];
+      } else {
+        qp[1] = qp[2] = qp[3] = R(0);
+      }
+      gradient_argument<R>(P, qp, Phim, Gs);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) Gs[s] -= Gm[s];
+    }
+    R dG[3][5];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int s = 0; s < 5; ++s) dG[d][s] = n[d] * Gs[s];
+    R gf[10];
+    gradient_flux<R>(P, dG, gPm, Gm[4], gf);
+#pragma unroll
+    for (int s = 0; s < 10; ++s) sFace[s][it] = sMvMI * gf[s];
+  }
+
+  // volume: strong-form gradient  xi_x * (D G)
+  R gfv[10];
+  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
+  if (tid < NP) {
+    const R *__restrict__ vg = A.vgeoP + (size_t)e * 10 * NP + tid;
+    R g[9];
+    const R MI = vg[(size_t)9 * NP];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) g[c] = vg[(size_t)c * NP] * MI;  // packed copy holds M*xi_x
+    R G1[5] = {0, 0, 0, 0, 0}, G2[5] = {0, 0, 0, 0, 0}, G3[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const R d1 = sD[i * NQ + n], d2 = sD[j * NQ + n], d3 = sD[k * NQ + n];
+      const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        G1[s] += d1 * sG[s][o1];
+        G2[s] += d2 * sG[s][o2];
+        G3[s] += d3 * sG[s][o3];
+      }
+    }
+    R dG[3][5];
+    const R vfac = P.horizontal_diffusion ? R(0) : R(1);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        dG[d][s] = g[d] * G1[s] + g[3 + d] * G2[s] + vfac * (g[6 + d] * G3[s]);
+    gradient_flux<R>(P, dG, gPhi, G[4], gfv);
+  }
+  __syncthreads();
+  if (tid < NP) {
+    const bool vert = !P.horizontal_diffusion;
+    if (i == 0)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][0 * NFP + j + NQ * k];
+    if (i == NQ - 1)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][1 * NFP + j + NQ * k];
+    if (j == 0)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][2 * NFP + i + NQ * k];
+    if (j == NQ - 1)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][3 * NFP + i + NQ * k];
+    if (vert && k == 0)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][4 * NFP + i + NQ * j];
+    if (vert && k == NQ - 1)
+      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][5 * NFP + i + NQ * j];
+    const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+    for (int s = 0; s < P.ngradflux; ++s) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// update! of LowStorageRungeKutta2N (LowStorageRungeKuttaMethod.jl:146-158)
+// ---------------------------------------------------------------------------------------
+template <class R>
+__global__ void lsrk_update_kernel(R *__restrict__ dQ, R *__restrict__ Q, R rka, R rkb, R dt,
+                                   size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const R d = dQ[i];
+    Q[i] += rkb * dt * d;
+    dQ[i] = d * rka;
+  }
+}
+
+template <class R>
+__global__ void scale_kernel(R *__restrict__ x, R a, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= a;
+}
+
+// kernel_fillsendbuf! / kernel_transferrecvbuf! (src/Arrays/MPIStateArrays.jl:837-871)
+// vmap holds 0-based linear node ids (converted once at bind time).
+template <class R>
+__global__ void pack_kernel(R *__restrict__ sendbuf, const R *__restrict__ buf,
+                            const int64_t *__restrict__ vmap, int64_t nmap, int Np, int nvar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmap) return;
+  const int64_t id = vmap[i];
+  const int64_t e = id / Np, n = id - e * Np;
+  for (int s = 0; s < nvar; ++s) sendbuf[i * nvar + s] = buf[(e * nvar + s) * Np + n];
+}
+template <class R>
+__global__ void unpack_kernel(R *__restrict__ buf, const R *__restrict__ recvbuf,
+                              const int64_t *__restrict__ vmap, int64_t nmap, int Np, int nvar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmap) return;
+  const int64_t id = vmap[i];
+  const int64_t e = id / Np, n = id - e * Np;
+  for (int s = 0; s < nvar; ++s) buf[(e * nvar + s) * Np + n] = recvbuf[i * nvar + s];
+}
+
+// Packed private geometry (built once in cmdg_bind_grid).
+//   vgeoP[e][c][n], c = 3*m + d : M * d(xi_{m+1})/d(x_{d+1});  c = 9 : MI
+//   (reference vgeo columns, Grids.jl:76-92: xi{m}x{d} at 3*(d-1)+(m-1), M = 9, MI = 10)
+template <class R>
+__global__ void pack_vgeo_kernel(R *__restrict__ out, const R *__restrict__ vgeo, int Np,
+                                 int nvgeo, size_t nreal) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nreal * Np) return;
+  const size_t e = idx / Np;
+  const int n = (int)(idx - e * Np);
+  const R *v = vgeo + e * (size_t)nvgeo * Np + n;
+  R *o = out + e * 10 * (size_t)Np + n;
+  const R M = v[(size_t)9 * Np];
+  for (int m = 0; m < 3; ++m)
+    for (int d = 0; d < 3; ++d) o[(size_t)(3 * m + d) * Np] = M * v[(size_t)(3 * d + m) * Np];
+  o[(size_t)9 * Np] = v[(size_t)10 * Np];
+}
+//   sgeoP[e][f][c][n], c = 0..2 unit normal, c = 3 : sM * vMI
+//   (reference sgeo[c, n, f, e], Grids.jl:129-146)
+template <class R>
+__global__ void pack_sgeo_kernel(R *__restrict__ out, const R *__restrict__ sgeo, int Nfp,
+                                 size_t nreal) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nreal * 6 * Nfp) return;
+  const size_t ef = idx / Nfp;
+  const int n = (int)(idx - ef * Nfp);
+  const R *s = sgeo + (ef * Nfp + n) * 5;
+  R *o = out + ef * 4 * (size_t)Nfp + n;
+  o[0] = s[0];
+  o[(size_t)Nfp] = s[1];
+  o[(size_t)2 * Nfp] = s[2];
+  o[(size_t)3 * Nfp] = s[3] * s[4];
+}
+
+}  // namespace cmdg

@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's DGModel / MPIStateArray / LSRK interface over libcmdg.
+
+* ``MPIStateArray``  <- src/Arrays/MPIStateArrays.jl:46-172 (``data`` is the reference's
+  ``Np x nstate x nelem`` array: a torch tensor of shape ``(nelem, nstate, Np)`` has the same bytes)
+* ``DiscontinuousSpectralElementGrid`` <- src/Numerics/Mesh/Grids.jl:170-265 (device arrays only)
+* ``DGModel``        <- src/Numerics/DGMethods/DGModel.jl:3-65, callable as ``:85-427``
+* ``LSRK54CarpenterKennedy``, ``LSRK144NiegemannDiehlBusch``, ``solve``, ``dostep``
+  <- src/Numerics/ODESolvers/LowStorageRungeKuttaMethod.jl, ODESolvers.jl:110-158
+
+PyTorch is used for device memory and streams only; all arithmetic on the path is done by the
+hand-written CUDA kernels in csrc/ through the C ABI.
+"""
+import ctypes as C
+from fractions import Fraction as Fr
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import balance_laws as bl
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DiscontinuousSpectralElementGrid:
+    """Device-resident grid arrays in the reference layout (1-based Int64 index arrays)."""
+
+    def __init__(self, N, vgeo, sgeo, vmapM, vmapP, elemtobndy, D, nrealelem,
+                 interiorelems=None, exteriorelems=None, vmapsend=None, vmaprecv=None,
+                 nabrtorank=(), nabrtovmapsend=(), nabrtovmaprecv=(), nvertelem=0,
+                 device="cuda"):
+        dev = torch.device(device)
+        self.N = int(N)
+        self.Nq = self.N + 1
+        self.Np = self.Nq ** 3
+        self.Nfp = self.Nq ** 2
+        tt = lambda a, dt=None: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+        self.vgeo = tt(vgeo)
+        self.sgeo = tt(sgeo)
+        self.FT = self.vgeo.dtype
+        self.nelem = self.vgeo.shape[0]
+        self.nrealelem = int(nrealelem)
+        assert self.vgeo.shape == (self.nelem, 25, self.Np)
+        assert self.sgeo.shape == (self.nelem, 6, self.Nfp, 5)
+        self.vmapM = tt(vmapM, torch.int64)
+        self.vmapP = tt(vmapP, torch.int64)
+        self.elemtobndy = tt(elemtobndy, torch.int64)
+        # D in Julia (column-major) memory order: element [a, b] at offset a + Nq*b
+        self.D = tt(np.asarray(D).T.copy()).to(self.FT)
+        if interiorelems is None:
+            interiorelems = np.arange(1, self.nrealelem + 1)
+            exteriorelems = np.zeros(0, dtype=np.int64)
+        self.interiorelems = tt(np.asarray(interiorelems, dtype=np.int64), torch.int64)
+        self.exteriorelems = tt(np.asarray(exteriorelems, dtype=np.int64), torch.int64)
+        z = np.zeros(0, dtype=np.int64)
+        self.vmapsend = tt(z if vmapsend is None else vmapsend, torch.int64)
+        self.vmaprecv = tt(z if vmaprecv is None else vmaprecv, torch.int64)
+        self.nabrtorank = [int(r) for r in nabrtorank]
+        self.nabrtovmapsend = [(int(a), int(b)) for a, b in nabrtovmapsend]
+        self.nabrtovmaprecv = [(int(a), int(b)) for a, b in nabrtovmaprecv]
+        self.nvertelem = int(nvertelem)
+        self.device = dev
+
+
+class MPIStateArray:
+    def __init__(self, grid, nstate, data=None):
+        self.grid = grid
+        self.nstate = nstate
+        if data is None:
+            self.data = torch.zeros((grid.nelem, nstate, grid.Np), dtype=grid.FT, device=grid.device)
+        else:
+            self.data = torch.as_tensor(np.ascontiguousarray(data)).to(grid.device).to(grid.FT)
+            assert self.data.shape == (grid.nelem, nstate, grid.Np)
+
+    @property
+    def realdata(self):
+        return self.data[:self.grid.nrealelem]
+
+    def similar(self):
+        return MPIStateArray(self.grid, self.nstate)
+
+    def weights(self):
+        return self.grid.vgeo[:, 9, :]  # vgeo[:, _M, :] (create_states.jl:16-17)
+
+
+def norm(Q, weighted=True):
+    """sqrt(sum M Q^2) over real elements (MPIStateArrays.jl:583-604), rank-local part."""
+    d = Q.realdata.double()
+    w = Q.weights()[:Q.grid.nrealelem, None, :].double() if weighted else 1.0
+    return float(torch.sqrt((d * d * w).sum()))
+
+
+def euclidean_distance(A, B):
+    d = (A.realdata - B.realdata).double()
+    w = A.weights()[:A.grid.nrealelem, None, :].double()
+    return float(torch.sqrt((d * d * w).sum()))
+
+
+_NF1 = {bl.RusanovNumericalFlux: _lib.NF_RUSANOV, bl.CentralNumericalFluxFirstOrder: _lib.NF_CENTRAL,
+        bl.RoeNumericalFlux: _lib.NF_ROE}
+
+
+class DGModel:
+    """``DGModel(balance_law, grid, nf1, nf2, nfgrad; state_auxiliary, ...)`` over libcmdg."""
+
+    def __init__(self, balance_law, grid, numerical_flux_first_order,
+                 numerical_flux_second_order, numerical_flux_gradient,
+                 state_auxiliary=None, state_gradient_flux=None,
+                 direction=None, diffusion_direction=None,
+                 skip_zero_viscosity=False, write_aux_diagnostics=True):
+        if not isinstance(balance_law, bl.AtmosModel):
+            raise bl.UnsupportedModelError(
+                f"balance law {type(balance_law).__name__} is not compiled into libcmdg")
+        balance_law.validate()
+        if type(numerical_flux_first_order) not in _NF1:
+            raise bl.UnsupportedModelError(
+                f"numerical flux {type(numerical_flux_first_order).__name__} is not supported")
+        if not isinstance(numerical_flux_second_order, bl.CentralNumericalFluxSecondOrder) or \
+                not isinstance(numerical_flux_gradient, bl.CentralNumericalFluxGradient):
+            raise bl.UnsupportedModelError("second-order/gradient fluxes must be Central")
+        if direction is not None and not isinstance(direction, bl.EveryDirection):
+            raise bl.UnsupportedModelError("only direction = EveryDirection() is supported")
+        self.balance_law = balance_law
+        self.grid = grid
+        self.numerical_flux_first_order = numerical_flux_first_order
+        self.numerical_flux_second_order = numerical_flux_second_order
+        self.numerical_flux_gradient = numerical_flux_gradient
+        self.diffusion_direction = diffusion_direction or bl.EveryDirection()
+        m = balance_law
+        A, GF = m.number_states("Auxiliary"), m.number_states("GradientFlux")
+        self.state_auxiliary = state_auxiliary or MPIStateArray(grid, A)
+        assert self.state_auxiliary.nstate == A, "state_auxiliary has the wrong number of columns"
+        self.state_gradient_flux = state_gradient_flux or MPIStateArray(grid, GF)
+        L = _lib.lib()
+        d = _lib.cmdg_desc()
+        d.struct_bytes = C.sizeof(_lib.cmdg_desc)
+        d.float_bytes = 8 if grid.FT == torch.float64 else 4
+        d.dim, d.N = 3, grid.N
+        d.nelem, d.nrealelem, d.nvertelem = grid.nelem, grid.nrealelem, grid.nvertelem
+        d.model = _lib.MODEL_ATMOS_DRY
+        d.nf_first = _NF1[type(numerical_flux_first_order)]
+        d.nf_second = d.nf_gradient = _lib.NF_CENTRAL
+        o = m.orientation
+        d.orientation = (_lib.ORIENT_NONE if isinstance(o, bl.NoOrientation) else
+                         _lib.ORIENT_FLAT if isinstance(o, bl.FlatOrientation) else _lib.ORIENT_SPHERICAL)
+        if isinstance(m.ref_state, bl.HydrostaticState):
+            d.ref_state, d.subtract_off = _lib.REF_HYDROSTATIC, int(m.ref_state.subtract_off)
+        else:
+            d.ref_state, d.subtract_off = _lib.REF_NONE, 0
+        t = m.turbulence
+        if isinstance(t, bl.ConstantKinematicViscosity):
+            d.turbulence, d.turb_param, d.turb_with_divergence = _lib.TURB_CONSTANT_KINEMATIC, t.ν, int(t.with_divergence)
+        elif isinstance(t, bl.ConstantDynamicViscosity):
+            d.turbulence, d.turb_param, d.turb_with_divergence = _lib.TURB_CONSTANT_DYNAMIC, t.ρν, int(t.with_divergence)
+        elif isinstance(t, bl.SmagorinskyLilly):
+            d.turbulence, d.turb_param = _lib.TURB_SMAGORINSKY, t.C_smag
+        else:
+            raise bl.UnsupportedModelError(f"turbulence closure {type(t).__name__} is not supported")
+        d.sources = sum({bl.Gravity: _lib.SRC_GRAVITY, bl.Coriolis: _lib.SRC_CORIOLIS}[type(s)]
+                        for s in m.source)
+        d.diffusion_direction = (_lib.DIR_HORIZONTAL if isinstance(self.diffusion_direction, bl.HorizontalDirection)
+                                 else _lib.DIR_EVERY)
+        d.skip_zero_viscosity = int(skip_zero_viscosity)
+        d.write_aux_diagnostics = int(write_aux_diagnostics)
+        d.nbc = len(m.boundaryconditions)
+        for i, bc in enumerate(m.boundaryconditions):
+            d.bc_kind[i] = _lib.BC_FREESLIP if isinstance(bc.momentum.drag, bl.FreeSlip) else _lib.BC_NOSLIP
+        d.nstate, d.naux = 5, A
+        d.ngrad, d.ngradflux = m.number_states("Gradient"), GF
+        p = m.param_set
+        d.R_d, d.cp_d, d.cv_d, d.T_0 = p.R_d, p.cp_d, p.cv_d, p.T_0
+        d.MSLP, d.grav, d.Omega, d.inv_Pr_turb = p.MSLP, p.grav, p.Omega, p.inv_Pr_turb
+        self._desc = d
+        self._h = C.c_void_p()
+        _lib.check(L.cmdg_create(C.byref(d), C.byref(self._h)))
+        g = grid
+        nn = len(g.nabrtorank)
+        ranks = (C.c_int32 * max(nn, 1))(*g.nabrtorank)
+        sr = (C.c_int64 * max(2 * nn, 1))(*[v for ab in g.nabrtovmapsend for v in ab])
+        rr = (C.c_int64 * max(2 * nn, 1))(*[v for ab in g.nabrtovmaprecv for v in ab])
+        _lib.check(L.cmdg_bind_grid(
+            self._h, _ptr(g.vgeo), _ptr(g.sgeo), _ptr(g.vmapM), _ptr(g.vmapP), _ptr(g.elemtobndy),
+            _ptr(g.D), _ptr(g.interiorelems), g.interiorelems.numel(), _ptr(g.exteriorelems),
+            g.exteriorelems.numel(), _ptr(g.vmapsend), g.vmapsend.numel(), _ptr(g.vmaprecv),
+            g.vmaprecv.numel(), ranks, sr, rr, nn), self._h)
+        _lib.check(L.cmdg_bind_state(self._h, _ptr(self.state_auxiliary.data),
+                                     _ptr(self.state_gradient_flux.data)), self._h)
+
+    # -- (dg::DGModel)(tendency, Q, param, t, alpha, beta) / (...; increment) ------------
+    def __call__(self, tendency, Q, param=None, t=0.0, α=1.0, β=0.0, increment=None):
+        if increment is not None:
+            α, β = 1.0, (1.0 if increment else 0.0)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().cmdg_tendency(self._h, _ptr(tendency.data), _ptr(Q.data), float(t),
+                                            float(α), float(β), C.c_void_p(st)), self._h)
+        # the reference returns after checked_wait (DGModel.jl:426)
+        torch.cuda.current_stream().synchronize()
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        _lib.check(_lib.lib().cmdg_comm_init(self._h, buf, rank, nranks), self._h)
+
+    def kernel_launches(self):
+        return int(_lib.lib().cmdg_kernel_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().cmdg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().cmdg_comm_unique_id(buf))
+    return buf.raw
+
+
+# ---------------------------------------------------------------------------------------
+# Low-storage RK
+# ---------------------------------------------------------------------------------------
+_LSRK54 = (
+    (Fr(0), Fr(-567301805773, 1357537059087), Fr(-2404267990393, 2016746695238),
+     Fr(-3550918686646, 2091501179385), Fr(-1275806237668, 842570457699)),
+    (Fr(1432997174477, 9575080441755), Fr(5161836677717, 13612068292357),
+     Fr(1720146321549, 2090206949498), Fr(3134564353537, 4481467310338),
+     Fr(2277821191437, 14882151754819)),
+    (Fr(0), Fr(1432997174477, 9575080441755), Fr(2526269341429, 6820363962896),
+     Fr(2006345519317, 3224310063776), Fr(2802321613138, 2924317926251)),
+)
+_LSRK144 = (
+    (0.0, -0.7188012108672410, -0.7785331173421570, -0.0053282796654044, -0.8552979934029281,
+     -3.9564138245774565, -1.5780575380587385, -2.0837094552574054, -0.7483334182761610,
+     -0.7032861106563359, 0.0013917096117681, -0.0932075369637460, -0.9514200470875948,
+     -7.1151571693922548),
+    (0.0367762454319673, 0.3136296607553959, 0.1531848691869027, 0.0030097086818182,
+     0.3326293790646110, 0.2440251405350864, 0.3718879239592277, 0.6204126221582444,
+     0.1524043173028741, 0.0760894927419266, 0.0077604214040978, 0.0024647284755382,
+     0.0780348340049386, 5.5059777270269628),
+    (0.0, 0.0367762454319673, 0.1249685262725025, 0.2446177702277698, 0.2476149531070420,
+     0.2969311120382472, 0.3978149645802642, 0.5270854589440328, 0.6981269994175695,
+     0.8190890835352128, 0.8527059887098624, 0.8604711817462826, 0.8627060376969976,
+     0.8734213127600976),
+)
+
+
+class LowStorageRungeKutta2N:
+    def __init__(self, rhs, RKA, RKB, RKC, Q, dt=0.0, t0=0.0):
+        FT = np.float64 if Q.data.dtype == torch.float64 else np.float32
+        conv = lambda xs: tuple(float(FT(x.numerator / x.denominator if isinstance(x, Fr) else x)) for x in xs)
+        self.rhs = rhs
+        self.RKA, self.RKB, self.RKC = conv(RKA), conv(RKB), conv(RKC)
+        self.dt, self.t, self.steps = float(dt), float(t0), 0
+        self.dQ = Q.similar()
+        ns = len(self.RKA)
+        arr = C.c_double * ns
+        self._a, self._b, self._c = arr(*self.RKA), arr(*self.RKB), arr(*self.RKC)
+
+    # dostep! with separate tendency and update kernels, exactly the reference's call sequence
+    def dostep_unfused(self, Q, time):
+        L = _lib.lib()
+        ns = len(self.RKA)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for s in range(ns):
+            self.rhs(self.dQ, Q, None, time + self.RKC[s] * self.dt, increment=True)
+            _lib.check(L.cmdg_lsrk_update(self.rhs._h, _ptr(self.dQ.data), _ptr(Q.data),
+                                          self.RKA[(s + 1) % ns], self.RKB[s], self.dt, st), self.rhs._h)
+        torch.cuda.current_stream().synchronize()
+
+    # dostep!: one fused kernel per stage (cmdg_lsrk_steps)
+    def dostep(self, Q, time, nsteps=1):
+        L = _lib.lib()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(L.cmdg_lsrk_steps(self.rhs._h, _ptr(Q.data), _ptr(self.dQ.data), float(time),
+                                     self.dt, len(self.RKA), self._a, self._b, self._c,
+                                     int(nsteps), st), self.rhs._h)
+
+    def general_dostep(self, Q, timeend, adjustfinalstep=True, fused=True):
+        time, dt = self.t, self.dt
+        final = False
+        if adjustfinalstep and time + dt > timeend:
+            orig, self.dt, final = dt, timeend - time, True
+        (self.dostep if fused else self.dostep_unfused)(Q, time)
+        if not final:
+            self.t = time + dt
+        else:
+            self.dt, self.t = orig, timeend
+        return self.t
+
+
+def LSRK54CarpenterKennedy(rhs, Q, dt=0.0, t0=0.0):
+    return LowStorageRungeKutta2N(rhs, *_LSRK54, Q, dt=dt, t0=t0)
+
+
+def LSRK144NiegemannDiehlBusch(rhs, Q, dt=0.0, t0=0.0):
+    return LowStorageRungeKutta2N(rhs, *_LSRK144, Q, dt=dt, t0=t0)
+
+
+def solve(Q, solver, timeend=float("inf"), numberofsteps=0, adjustfinalstep=True, fused=True,
+          callbacks=()):
+    """``solve!`` (ODESolvers.jl:110-158).  Without callbacks and with a fixed number of steps the
+    whole loop runs inside one cmdg_lsrk_steps call."""
+    assert np.isfinite(timeend) or numberofsteps > 0
+    if fused and not callbacks and numberofsteps > 0 and not np.isfinite(timeend):
+        solver.dostep(Q, solver.t, nsteps=numberofsteps)
+        solver.t += numberofsteps * solver.dt
+        solver.steps = numberofsteps
+        torch.cuda.current_stream().synchronize()
+        return solver.t
+    step, time = 0, solver.t
+    while time < timeend:
+        step += 1
+        solver.steps = step
+        time = solver.general_dostep(Q, timeend, adjustfinalstep, fused)
+        for cb in callbacks:
+            cb(solver, Q, time)
+        if step == numberofsteps:
+            break
+    torch.cuda.current_stream().synchronize()
+    return solver.t

@@ -1,0 +1,144 @@
+"""Shared harness of the GPU parity tests: builds a case with the CPU oracle, hands the *same*
+arrays (byte-identical layout) to libcmdg through the Python mirror of the DGModel interface,
+and returns the differences."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import topologies as tp, grids as ogrids, atmos as oatmos, dgmodel as odg  # noqa: E402
+from oracle import odesolvers as oode, mpistatearrays as omsa  # noqa: E402
+
+
+def pkg():
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(np.sum((a - b) ** 2) / max(np.sum(b ** 2), 1e-300)))
+
+
+def device_grid(g, device="cuda"):
+    """oracle Grid -> device grid with the reference's array layouts."""
+    P = pkg()
+    return P.DiscontinuousSpectralElementGrid(
+        g.N[0], g.vgeo, g.sgeo, g.vmapM, g.vmapP, g.elemtobndy, g.D[0], g.nreal,
+        interiorelems=g.interiorelems, exteriorelems=g.exteriorelems,
+        vmapsend=g.vmapsend, vmaprecv=g.vmaprecv, nabrtorank=g.nabrtorank,
+        nabrtovmapsend=g.nabrtovmapsend, nabrtovmaprecv=g.nabrtovmaprecv,
+        nvertelem=g.topology.stacksize, device=device)
+
+
+NF = {"rusanov": "RusanovNumericalFlux", "central": "CentralNumericalFluxFirstOrder",
+      "roe": "RoeNumericalFlux"}
+
+
+def device_model(om):
+    """oracle DryAtmosModel -> package AtmosModel."""
+    P = pkg()
+    orient = {"none": P.NoOrientation, "flat": P.FlatOrientation, "spherical": P.SphericalOrientation}[om.orientation]()
+    if om.ref_state is None:
+        ref = P.NoReferenceState()
+    else:
+        ref = P.HydrostaticState(P.DecayingTemperatureProfile(om.ref_state["T_surf"], om.ref_state["T_min"],
+                                                            om.ref_state["H_t"]),
+                                 subtract_off=om.ref_state.get("subtract_off", True))
+    k = om.turbulence
+    turb = {"constant_dynamic": lambda: P.ConstantDynamicViscosity(float(k[1]), bool(k[2])),
+            "constant_kinematic": lambda: P.ConstantKinematicViscosity(float(k[1]), bool(k[2])),
+            "smagorinsky": lambda: P.SmagorinskyLilly(float(k[1]))}[k[0]]()
+    src = tuple({"gravity": P.Gravity, "coriolis": P.Coriolis}[s]() for s in om.sources)
+    bcs = tuple(P.AtmosBC(P.Impenetrable(P.FreeSlip() if b == "freeslip" else P.NoSlip())) for b in om.bcs)
+    return P.AtmosModel(orientation=orient, ref_state=ref, turbulence=turb, source=src,
+                        boundaryconditions=bcs)
+
+
+def make_device_dg(odgm, g, nf, diffusion_direction="every", skip_zero_viscosity=False):
+    P = pkg()
+    dgrid = device_grid(g)
+    m = device_model(odgm.bl)
+    aux = P.MPIStateArray(dgrid, odgm.bl.A, data=odgm.state_auxiliary[0].data)
+    dd = P.HorizontalDirection() if diffusion_direction == "horizontal" else P.EveryDirection()
+    dg = P.DGModel(m, dgrid, getattr(P, NF[nf])(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux,
+                   diffusion_direction=dd, skip_zero_viscosity=skip_zero_viscosity)
+    return dg, dgrid
+
+
+def compare_case(model, g, Q0, nf="rusanov", nsteps=1, dt=None, diffusion_direction="every",
+                 skip_zero_viscosity=False, t=0.0):
+    """Single-rank comparison of (i) one tendency evaluation with beta = 0 and with increment,
+    (ii) ``nsteps`` LSRK54 steps, between the oracle and libcmdg.  ``Q0``: (S, nreal, Np)."""
+    P = pkg()
+    FT = g.FT
+    odgm = odg.DGModel(model, [g], nf, diffusion_direction=diffusion_direction,
+                       skip_zero_viscosity=skip_zero_viscosity)
+    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
+    omsa.ghost_exchange([oQ])
+    dg, dgrid = make_device_dg(odgm, g, nf, diffusion_direction, skip_zero_viscosity)
+    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    # (i) tendency, beta = 0
+    odQ = oQ.similar()
+    odgm([odQ], [oQ], t, 1, 0)
+    dT = P.MPIStateArray(dgrid, 5)
+    dT.data.fill_(float("nan"))   # beta = 0 must not read the old tendency
+    dg(dT, dQ, None, t, 1.0, 0.0)
+    res = {"tendency_rel_l2": rel_l2(dT.realdata.cpu().numpy(), odQ.realdata)}
+    if model.GF > 0 and not (skip_zero_viscosity and not model.viscous()):
+        res["gradflux_rel_l2"] = rel_l2(dg.state_gradient_flux.realdata.cpu().numpy(),
+                                        odgm.state_gradient_flux[0].realdata)
+    res["aux_theta_T_rel_l2"] = rel_l2(
+        dg.state_auxiliary.realdata[:, [model.a_θv, model.a_T]].cpu().numpy(),
+        odgm.state_auxiliary[0].realdata[:, [model.a_θv, model.a_T]])
+    # increment form with alpha != 1
+    odgm([odQ], [oQ], t, 0.5, 2.0)
+    dg(dT, dQ, None, t, 0.5, 2.0)
+    res["tendency_inc_rel_l2"] = rel_l2(dT.realdata.cpu().numpy(), odQ.realdata)
+    # (ii) time stepping
+    if nsteps > 0:
+        osol = oode.LSRK54CarpenterKennedy(odgm, [oQ], dt=dt, t0=t)
+        oode.solve([oQ], osol, numberofsteps=nsteps)
+        dsol = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt, t0=t)
+        dQ2 = P.MPIStateArray(dgrid, 5, data=dQ.data.cpu().numpy())
+        P.solve(dQ, dsol, numberofsteps=nsteps)
+        res["state_rel_l2"] = rel_l2(dQ.realdata.cpu().numpy(), oQ.realdata)
+        # the un-fused call sequence (cmdg_tendency + cmdg_lsrk_update) must agree as well
+        dsol2 = P.LSRK54CarpenterKennedy(dg, dQ2, dt=dt, t0=t)
+        P.solve(dQ2, dsol2, numberofsteps=min(nsteps, 2), fused=False)
+        if nsteps <= 2:
+            res["state_unfused_rel_l2"] = rel_l2(dQ2.realdata.cpu().numpy(), oQ.realdata)
+        res["dQ_after_step_max"] = float(dsol.dQ.realdata.abs().max())
+    res["launches"] = dg.kernel_launches()
+    dg.close()
+    return res
+
+
+def vortex_setup(nelem=(5, 5, 1), FT=np.float64, csize=1):
+    ps = oatmos.Params(FT)
+    setup = oatmos.IsentropicVortexSetup(ps, FT)
+    L = setup.domain_halflength
+    br = tuple(np.linspace(-L, L, n + 1).astype(FT) for n in nelem)
+    topos = tp.BrickTopology(csize, br, periodicity=(True, True, True))
+    gs = [ogrids.Grid(t, 4, FT=FT) for t in topos]
+    model = oatmos.DryAtmosModel(FT, orientation="none", ref_state=None,
+                                 turbulence=("constant_dynamic", 0.0, False), sources=())
+    elementsize = min(float(np.min(np.diff(b))) for b in br)
+    dt = elementsize / float(oatmos.soundspeed_air(ps, setup.T_inf)) / 4 ** 2
+    return model, gs, setup, dt
+
+
+def vortex_case(nelem=(5, 5, 1), nf="rusanov", nsteps=1, FT=np.float64, skip_zero_viscosity=True):
+    model, gs, setup, dt = vortex_setup(nelem, FT)
+    g = gs[0]
+    Q0 = setup(g.vgeo[:g.nreal, ogrids._x1], g.vgeo[:g.nreal, ogrids._x2],
+               g.vgeo[:g.nreal, ogrids._x3], FT(0))
+    return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                        skip_zero_viscosity=skip_zero_viscosity)
