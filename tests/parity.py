@@ -140,5 +140,116 @@ def vortex_case(nelem=(5, 5, 1), nf="rusanov", nsteps=1, FT=np.float64, skip_zer
     g = gs[0]
     Q0 = setup(g.vgeo[:g.nreal, ogrids._x1], g.vgeo[:g.nreal, ogrids._x2],
                g.vgeo[:g.nreal, ogrids._x3], FT(0))
+    res = compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                       skip_zero_viscosity=skip_zero_viscosity)
+    if FT == np.float32:
+        res.update(float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity))
+    return res
+
+
+def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity):
+    """Float32 conditioning check: evaluate the oracle in Float64 on the *same Float32 inputs*
+    (grid arrays and state upcast) and report the Float32 oracle's and libcmdg's errors
+    against that truth.  The isentropic vortex lives on a 0.1 m box, so a Float32 tendency
+    carries ~1e-5 of rounding whatever the evaluation order."""
+    import copy
+    P = pkg()
+    g64 = copy.copy(g)
+    g64.FT = np.float64
+    g64.vgeo, g64.sgeo = g.vgeo.astype(np.float64), g.sgeo.astype(np.float64)
+    g64.D = [d.astype(np.float64) for d in g.D]
+    m64 = oatmos.DryAtmosModel(np.float64, orientation=model.orientation, ref_state=model.ref_state,
+                               turbulence=model.turbulence, sources=model.sources, bcs=model.bcs)
+    out = {}
+    tend = {}
+    for name, gg, mm in (("truth", g64, m64), ("oracle32", g, model)):
+        dgm = odg.DGModel(mm, [gg], nf, skip_zero_viscosity=skip_zero_viscosity)
+        q = omsa.MPIStateArray.from_grid(gg, 5)
+        np.moveaxis(q.data[:gg.nreal], 1, 0)[...] = Q0
+        omsa.ghost_exchange([q])
+        dq = q.similar()
+        dgm([dq], [q], 0.0, 1, 0)
+        tend[name] = dq.realdata.astype(np.float64)
+        if name == "oracle32":
+            dg, dgrid = make_device_dg(dgm, gg, nf, skip_zero_viscosity=skip_zero_viscosity)
+            dQ = P.MPIStateArray(dgrid, 5, data=q.data)
+            dT = P.MPIStateArray(dgrid, 5)
+            dg(dT, dQ, None, 0.0, 1.0, 0.0)
+            tend["cuda32"] = dT.realdata.cpu().numpy().astype(np.float64)
+            dg.close()
+    out["oracle32_vs_truth"] = rel_l2(tend["oracle32"], tend["truth"])
+    out["cuda32_vs_truth"] = rel_l2(tend["cuda32"], tend["truth"])
+    return out
+
+
+def gcm_setup(ne=3, nvert=2, FT=np.float64, turbulence=("constant_kinematic", 0.0, False),
+              csize=1, domain_height=30e3):
+    """Dry baroclinic wave on the cubed sphere (experiments/TestCase/baroclinic_wave.jl with
+    explicit stepping, no hyperdiffusion): spherical orientation, hydrostatic reference state
+    (DecayingTemperatureProfile 290/220/8 km), Gravity + Coriolis, free-slip walls."""
+    ps = oatmos.Params(FT)
+    a = float(ps.planet_radius)
+    Rrange = np.linspace(a, a + domain_height, nvert + 1)
+    topos = tp.StackedCubedSphereTopology(csize, ne, Rrange, boundary=(1, 2))
+    gs = [ogrids.Grid(t, 4, FT=FT, meshwarp=tp.equiangular_cubed_sphere_warp) for t in topos]
+    model = oatmos.DryAtmosModel(
+        FT, orientation="spherical",
+        ref_state=dict(T_surf=290.0, T_min=220.0, H_t=8e3, subtract_off=True),
+        turbulence=turbulence, sources=("gravity", "coriolis"), bcs=("freeslip", "freeslip"))
+    return model, gs
+
+
+def gcm_case(nf="rusanov", nsteps=1, dt=0.5, turbulence=("constant_kinematic", 0.0, False),
+             diffusion_direction="every", skip_zero_viscosity=True, ne=3, nvert=2):
+    model, gs = gcm_setup(ne, nvert, turbulence=turbulence)
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], nf)
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_baroclinic_wave(model, aux)
     return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                        diffusion_direction=diffusion_direction,
                         skip_zero_viscosity=skip_zero_viscosity)
+
+
+def box_setup(nelem=(3, 2, 3), FT=np.float64, turbulence=("smagorinsky", 0.21), csize=1,
+              periodic_z=False):
+    """LES-like box (tutorials/Atmos/risingbubble.jl without tracers): flat orientation,
+    hydrostatic reference state, gravity, walls top/bottom, periodic horizontally."""
+    br = (np.linspace(0, 1500, nelem[0] + 1), np.linspace(0, 1000, nelem[1] + 1),
+          np.linspace(0, 1500, nelem[2] + 1))
+    topos = tp.StackedBrickTopology(csize, br, periodicity=(True, True, periodic_z),
+                                    boundary=((0, 0), (0, 0), (1, 2)))
+    gs = [ogrids.Grid(t, 4, FT=FT) for t in topos]
+    model = oatmos.DryAtmosModel(
+        FT, orientation="flat",
+        ref_state=dict(T_surf=300.0, T_min=220.0, H_t=8e3, subtract_off=True),
+        turbulence=turbulence, sources=("gravity",), bcs=("freeslip", "noslip"))
+    return model, gs
+
+
+def bubble_state(model, g, aux):
+    """Warm bubble + sheared wind on top of the reference state (smooth, non-trivial gradients)."""
+    ps = model.ps
+    FT = g.FT
+    x, y, z = aux[0], aux[1], aux[2]
+    r = np.sqrt((x - 750) ** 2 + (z - 500) ** 2 + (y - 500) ** 2) / 400
+    dT = np.where(r < 1, 2.0 * np.cos(np.pi * r / 2) ** 2, 0.0)
+    Tref = aux[model.a_ref["T"]]
+    p = aux[model.a_ref["p"]]
+    T = Tref + dT
+    ρ = oatmos.air_density(ps, T, p)
+    u = [5 + 3 * np.sin(2 * np.pi * z / 1500), 2 * np.cos(2 * np.pi * x / 1500), 1.5 * np.sin(2 * np.pi * y / 1000) * np.sin(np.pi * z / 1500)]
+    e_kin = 0.5 * (u[0] ** 2 + u[1] ** 2 + u[2] ** 2)
+    e_tot = oatmos.total_energy(ps, e_kin, aux[model.a_Φ], T)
+    return np.stack([ρ, ρ * u[0], ρ * u[1], ρ * u[2], ρ * e_tot]).astype(FT)
+
+
+def box_case(nf="rusanov", nsteps=1, dt=0.01, turbulence=("smagorinsky", 0.21),
+             diffusion_direction="every", nelem=(3, 2, 3)):
+    model, gs = box_setup(nelem, turbulence=turbulence)
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], nf, diffusion_direction=diffusion_direction)
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = bubble_state(model, g, aux)
+    return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                        diffusion_direction=diffusion_direction)
