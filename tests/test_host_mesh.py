@@ -1,0 +1,150 @@
+"""The harness's vectorised mesh/grid builders (climatemachine.jl_b200/topologies.py, grids.py)
+against the oracle: connectivity bit-exact, geometry to rounding."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+from oracle import topologies as otp, brickmesh as obm, grids as ogrids
+
+P = ge.load_package()
+from climatemachine_jl_b200 import topologies as ptp  # noqa: E402
+
+FIELDS = ["elemtoelem", "elemtoface", "elemtoordr", "elemtobndy", "sendelems", "ghostfaces",
+          "sendfaces", "interiorelems", "exteriorelems", "elemtocoord"]
+
+
+def same_topology(a, b):
+    assert (a.nelem, a.nreal, a.nghost) == (b.nelem, b.nreal, b.nghost)
+    for f in FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.shape == y.shape, f
+        assert np.array_equal(x, y), f
+    assert list(a.nabrtorank) == list(b.nabrtorank)
+    assert list(a.nabrtorecv) == list(b.nabrtorecv)
+    assert list(a.nabrtosend) == list(b.nabrtosend)
+
+
+def test_hilbert_codes_match_scalar_version():
+    rng = np.random.default_rng(0)
+    for d in (2, 3):
+        X = rng.integers(0, 2 ** 63, size=(200, d), dtype=np.uint64) * np.uint64(2) + \
+            rng.integers(0, 2, size=(200, d), dtype=np.uint64)
+        H = ptp.hilbert_codes(X)
+        for r in range(200):
+            assert [int(v) for v in H[r]] == obm.hilbertcode([int(v) for v in X[r]])
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("periodic", [(True, True, True), (False, True, False)])
+def test_brick_topology_3d(nranks, periodic):
+    br = (np.linspace(0, 1, 5), np.linspace(-1, 1, 4), np.linspace(2, 3, 3))
+    bnd = ((1, 2), (3, 4), (5, 6))
+    ref = otp.BrickTopology(nranks, br, boundary=bnd, periodicity=periodic)
+    for r in range(nranks):
+        same_topology(ptp.brick_topology(br, periodic, bnd, r, nranks), ref[r])
+
+
+@pytest.mark.parametrize("conn", ["face", "full"])
+def test_brick_topology_2d_golden_mesh(conn):
+    br = (np.arange(0, 5), np.arange(5, 10))
+    ref = otp.BrickTopology(3, br, boundary=((1, 2), (3, 4)), periodicity=(False, True),
+                            connectivity=conn)
+    for r in range(3):
+        same_topology(ptp.brick_topology(br, (False, True), ((1, 2), (3, 4)), r, 3, conn), ref[r])
+
+
+@pytest.mark.parametrize("nranks,conn", [(1, "full"), (2, "full"), (3, "face"), (4, "full")])
+def test_stacked_cubed_sphere_topology(nranks, conn):
+    R = np.array([1.0, 1.5, 2.5])
+    ref = otp.StackedCubedSphereTopology(nranks, 4, R, boundary=(1, 2), connectivity=conn)
+    for r in range(nranks):
+        same_topology(ptp.stacked_cubed_sphere_topology(4, R, (1, 2), r, nranks, conn), ref[r])
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_stacked_brick_topology(nranks):
+    br = (np.linspace(0, 4, 5), np.linspace(0, 3, 4), np.linspace(0, 2, 3))
+    per, bnd = (True, False, False), ((0, 0), (1, 2), (3, 4))
+    ref = otp.StackedBrickTopology(nranks, br, periodicity=per, boundary=bnd)
+    for r in range(nranks):
+        same_topology(ptp.stacked_brick_topology(br, per, bnd, r, nranks), ref[r])
+
+
+from climatemachine_jl_b200 import grids as pgrids, atmos_init as pinit  # noqa: E402
+import torch  # noqa: E402
+
+
+def _same_grid(pg, og, tol=3e-12):
+    assert np.array_equal(pg.vmapM.numpy(), og.vmapM)
+    assert np.array_equal(pg.vmapP.numpy(), og.vmapP)
+    assert np.array_equal(pg.elemtobndy.numpy(), og.elemtobndy)
+    assert np.array_equal(pg.vmapsend.numpy(), og.vmapsend)
+    assert np.array_equal(pg.vmaprecv.numpy(), og.vmaprecv)
+    assert pg.nabrtovmapsend == og.nabrtovmapsend and pg.nabrtovmaprecv == og.nabrtovmaprecv
+    assert np.allclose(pg.D_host, og.D[0], rtol=0, atol=1e-14)
+    vg, ovg = pg.vgeo.numpy(), og.vgeo
+    scale = np.abs(ovg).max(axis=(0, 2), keepdims=True) + 1e-300
+    scale[:, 0:9] = scale[:, 0:9].max()      # metric terms share one scale (some are ~0)
+    scale[:, 16:25] = scale[:, 16:25].max()
+    scale[:, 12:15] = scale[:, 12:15].max()
+    assert np.max(np.abs(vg - ovg) / scale) < tol
+    sg, osg = pg.sgeo.numpy(), og.sgeo
+    scale = np.abs(osg).max(axis=(0, 1, 2), keepdims=True)
+    scale[..., 0:3] = 1.0
+    assert np.max(np.abs(sg - osg) / scale) < tol
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_grid_arrays_box(nranks):
+    br = (np.linspace(-1, 1, 4), np.linspace(0, 3, 3), np.linspace(0, 1, 3))
+    for r in range(nranks):
+        ot = otp.BrickTopology(nranks, br, periodicity=(True, True, True))[r]
+        pt = ptp.brick_topology(br, (True, True, True), None, r, nranks)
+        _same_grid(pgrids.build_grid(pt, 4, device="cpu"), ogrids.Grid(ot, 4))
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_grid_arrays_cubed_sphere_and_aux(nranks):
+    from oracle import atmos as oatmos, dgmodel as odg
+    a = 6.371e6
+    R = np.linspace(a, a + 30e3, 3)
+    ots = otp.StackedCubedSphereTopology(nranks, 3, R, boundary=(1, 2))
+    ogs = [ogrids.Grid(t, 4, meshwarp=otp.equiangular_cubed_sphere_warp) for t in ots]
+    om = oatmos.DryAtmosModel(np.float64, orientation="spherical",
+                              ref_state=dict(T_surf=290.0, T_min=220.0, H_t=8e3, subtract_off=True),
+                              turbulence=("smagorinsky", 0.21), sources=("gravity", "coriolis"),
+                              bcs=("freeslip", "freeslip"))
+    odgm = odg.DGModel(om, ogs, "rusanov")
+    pm = P.AtmosModel(orientation=P.SphericalOrientation(),
+                      ref_state=P.HydrostaticState(P.DecayingTemperatureProfile(290.0, 220.0, 8e3)),
+                      turbulence=P.SmagorinskyLilly(0.21), source=(P.Gravity(), P.Coriolis()),
+                      boundaryconditions=(P.AtmosBC(), P.AtmosBC()))
+    pgs = [pgrids.build_grid(ptp.stacked_cubed_sphere_topology(3, R, (1, 2), r, nranks), 4,
+                             meshwarp=ptp.cubed_sphere_warp, device="cpu") for r in range(nranks)]
+    for pg, og in zip(pgs, ogs):
+        _same_grid(pg, og, tol=1e-9)  # thin shell at r = 6.4e6 m: D*x cancels ~5 digits
+    if nranks == 1:
+        aux = pinit.init_state_auxiliary(pm, pgs[0])
+        oa = odgm.state_auxiliary[0].data
+        pa = aux.data.numpy()
+        nr = ogs[0].nreal
+        scale = np.abs(oa[:nr]).max(axis=(0, 2), keepdims=True) + 1e-300
+        err = np.abs(pa[:nr] - oa[:nr]) / scale
+        # theta_v / air_T (last two columns) are filled by the first tendency evaluation
+        assert err[:, :-2].max() < 1e-9, err.max(axis=(0, 2))
+        Q = pinit.baroclinic_wave(pm, pgs[0], aux).numpy()
+        oQ = oatmos.init_baroclinic_wave(om, np.moveaxis(oa[:nr], 1, 0))
+        assert np.allclose(Q, np.moveaxis(oQ, 0, 1), rtol=1e-9, atol=1e-9)
+
+
+def test_vortex_initial_condition():
+    from oracle import atmos as oatmos
+    br = tuple(np.linspace(-0.05, 0.05, n + 1) for n in (3, 3, 2))
+    pt = ptp.brick_topology(br, (True, True, True))
+    pg = pgrids.build_grid(pt, 4, device="cpu")
+    Q = pinit.isentropic_vortex(P.AtmosModel(), pg, 0.0).numpy()
+    ps = oatmos.Params()
+    setup = oatmos.IsentropicVortexSetup(ps)
+    vg = pg.vgeo.numpy()
+    oQ = setup(vg[:, 12], vg[:, 13], vg[:, 14], 0.0)
+    assert np.allclose(Q, np.moveaxis(oQ, 0, 1), rtol=1e-13)
