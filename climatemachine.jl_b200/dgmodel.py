@@ -205,6 +205,25 @@ class DGModel:
     def kernel_launches(self):
         return int(_lib.lib().cmdg_kernel_launches(self._h))
 
+    # begin_ghost_exchange! + end_ghost_exchange! (MPIStateArrays.jl:411-483)
+    def ghost_exchange(self, arr):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L = _lib.lib()
+        _lib.check(L.cmdg_exchange_begin(self._h, _ptr(arr.data), arr.nstate, st), self._h)
+        _lib.check(L.cmdg_exchange_end(self._h, _ptr(arr.data), arr.nstate, st), self._h)
+        torch.cuda.current_stream().synchronize()
+
+    def set_timing(self, enable=True):
+        _lib.check(_lib.lib().cmdg_set_timing(self._h, int(enable)), self._h)
+
+    def last_kernel_ms(self):
+        n = C.c_int64(0)
+        ms = _lib.lib().cmdg_last_kernel_ms(self._h, C.byref(n))
+        return float(ms), int(n.value)
+
+    def sync(self):
+        _lib.check(_lib.lib().cmdg_sync(self._h), self._h)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             _lib.lib().cmdg_destroy(self._h)
@@ -281,6 +300,13 @@ class LowStorageRungeKutta2N:
         _lib.check(L.cmdg_lsrk_steps(self.rhs._h, _ptr(Q.data), _ptr(self.dQ.data), float(time),
                                      self.dt, len(self.RKA), self._a, self._b, self._c,
                                      int(nsteps), st), self.rhs._h)
+
+    # the same through HOST buffers (cmdg_lsrk_steps_host): realview(Q) as a pinned CPU tensor
+    def dostep_host(self, Q_host, time, nsteps=1):
+        assert Q_host.device.type == "cpu" and Q_host.is_contiguous()
+        _lib.check(_lib.lib().cmdg_lsrk_steps_host(
+            self.rhs._h, C.c_void_p(Q_host.data_ptr()), float(time), self.dt, len(self.RKA),
+            self._a, self._b, self._c, int(nsteps)), self.rhs._h)
 
     def general_dostep(self, Q, timeend, adjustfinalstep=True, fused=True):
         time, dt = self.t, self.dt

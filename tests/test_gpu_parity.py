@@ -98,3 +98,21 @@ def test_held_suarez_like_smagorinsky_sphere():
     assert res["gradflux_rel_l2"] <= 1e-12, res
     assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
     assert res["state_rel_l2"] <= 1e-12, res
+
+
+def test_multi_gpu_halo_and_parity():
+    """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU box skips it, `gpurun --gpus 2` runs it)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29511",
+         os.path.join(root, "tests", "multi_gpu_parity.py")],
+        capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("MULTI_GPU_PARITY") == 3
