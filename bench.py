@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -69,9 +69,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,7 +80,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        inside = [s for (t, s) in self.samples if t0 is not None and t0 <= t <= t1]
+        where = "timed region"
+        if len(inside) < 3:   # short region: use every sample since the warm-up started (GPU busy)
+            inside, where = [s for (_, s) in self.samples], "warm-up + timed region"
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 8:
                 continue
@@ -95,7 +99,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 # ----------------------------------------------------------------------------------------
@@ -172,24 +176,31 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
     sol.dostep(Q, 0.0, nsteps=max(args.warmup, 3))
     barrier()
     norm0 = P.norm(Q)
-    clocks = ClockSampler(local)
-    clocks.start()
+    # keep the GPU busy until the sampler has produced its first lines (nvidia-smi start-up)
+    t_w = time.perf_counter()
+    while len(clocks.samples) < 2 and time.perf_counter() - t_w < 3.0:
+        sol.dostep(Q, 0.0, nsteps=5)
+        torch.cuda.synchronize()
     dg.set_timing(True)
     l0 = dg.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tc0 = time.perf_counter()
     e0.record()
     sol.dostep(Q, 0.0, nsteps=args.steps)
     e1.record()
     barrier()
+    tc1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = dg.kernel_launches() - l0
     kern_ms, kern_n = dg.last_kernel_ms()
     dg.set_timing(False)
-    clk = clocks.stop()
+    clk = clocks.stop(tc0, tc1)
     norm1 = P.norm(Q)
     assert np.isfinite(norm1), "state blew up"
 
@@ -370,7 +381,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex"])
