@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmdg.so")
+LIB_PATH = os.environ.get("CMDG_LIB", os.path.join(_HERE, "libcmdg.so"))  # CMDG_LIB: dev override
 
 CMDG_F32, CMDG_F64 = 4, 8
 MODEL_ATMOS_DRY, MODEL_HB = 1, 2
