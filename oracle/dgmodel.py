@@ -79,6 +79,10 @@ class DGModel:
 
     def init_state_auxiliary(self):
         bl = self.bl
+        if hasattr(bl, "init_state_auxiliary"):
+            bl.init_state_auxiliary(self)
+            ghost_exchange(self.state_auxiliary)
+            return
         ps = bl.ps
         # Orientation (Orientations.jl init_aux!)
         for g, aux in zip(self.grids, self.state_auxiliary):
@@ -182,6 +186,9 @@ class DGModel:
 
     def update_auxiliary_state(self, Q, elems="real"):
         bl = self.bl
+        if hasattr(bl, "update_auxiliary_state"):
+            bl.update_auxiliary_state(self, Q, elems)
+            return
         for g, q, aux in zip(self.grids, Q, self.state_auxiliary):
             sl = slice(0, g.nreal) if elems == "real" else slice(g.nreal, g.nelem)
             qs = _sv(q.data[sl])
@@ -260,7 +267,10 @@ class DGModel:
             return fl
         if self.nf1 == "rusanov":
             λ = np.maximum(bl.wavespeed(n, Qm, am), bl.wavespeed(n, Qp, ap))
-            return fl + (λ * (Qm - Qp)) / 2
+            penalty = λ * (Qm - Qp)
+            if hasattr(bl, "update_penalty"):
+                bl.update_penalty(penalty)
+            return fl + penalty / 2
         if self.nf1 == "roe":
             return fl - bl.roe_dissipation(n, Qm, am, Qp, ap)
         raise ValueError(self.nf1)
@@ -309,7 +319,15 @@ class DGModel:
                     ap2 = np.moveaxis(aux.data[ep, :, vp], -1, 0)
                     F2 = F2 + bl.flux_second_order(Qp2, gp, ap2)
                     fl2 = F2[0] * (n[0] / 2) + F2[1] * (n[1] / 2) + F2[2] * (n[2] / 2)
-                    fl2[:, isb] = 0  # FreeSlip/NoSlip + Insulating: no diffusive boundary flux
+                    # AtmosBC FreeSlip/NoSlip + Insulating: no diffusive boundary flux; models with
+                    # flux-based BCs (normal_boundary_flux_second_order!, NumericalFluxes.jl:872-967)
+                    # provide the full plus-side flux
+                    fl2[:, isb] = 0
+                    if hasattr(bl, "boundary_flux_second_order"):
+                        for tag in np.unique(bnd[isb]):
+                            m = bnd == tag
+                            Fb = bl.boundary_flux_second_order(int(tag), n[:, m], Qm[:, m], gm[:, m], am[:, m])
+                            fl2[:, m] = Fb[0] * n[0][m] + Fb[1] * n[1][m] + Fb[2] * n[2][m]
                     fl = fl + fl2
                 for s in range(bl.S):
                     cur = dq.data[em, s, vm]
@@ -396,8 +414,12 @@ class DGModel:
             self.update_auxiliary_state(Q, "ghost")   # after end_ghost_exchange!(Q)
             self.interface_gradients(Q, t, "exterior")
             ghost_exchange(self.state_gradient_flux)
+            if hasattr(bl, "update_auxiliary_state_gradient"):
+                bl.update_auxiliary_state_gradient(self, Q, "real")
         self.volume_tendency(tendency, Q, t, α, β)
         self.interface_tendency(tendency, Q, t, α, "interior")
+        if second and hasattr(bl, "update_auxiliary_state_gradient"):
+            bl.update_auxiliary_state_gradient(self, Q, "ghost")
         if not second:
             self.update_auxiliary_state(Q, "ghost")
         self.interface_tendency(tendency, Q, t, α, "exterior")
