@@ -39,6 +39,18 @@ class cmdg_desc(C.Structure):
     ]
 
 
+class cmdg_ocean_desc(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("nbc", C.c_int32), ("bc_velocity", C.c_int32 * 6),
+                ("bc_temperature", C.c_int32 * 6)] + \
+               [(n, C.c_double) for n in ("grav", "rho0", "ch", "cz", "alphaT", "nuh", "nuz", "kappah",
+                                          "kappaz", "kappac", "f0", "beta", "Lx", "Ly", "H", "tau0",
+                                          "lambda_r", "thetaE")]
+
+
+OCEAN_VEL_NOSLIP, OCEAN_VEL_FREESLIP, OCEAN_VEL_PENETRABLE_FREESLIP, OCEAN_VEL_PENETRABLE_KINEMATIC_STRESS = 1, 2, 3, 4
+OCEAN_TEMP_INSULATING, OCEAN_TEMP_FLUX = 1, 2
+
+
 class CmdgError(RuntimeError):
     pass
 
@@ -51,7 +63,7 @@ SYMBOLS = [
     "cmdg_bind_state", "cmdg_tendency", "cmdg_lsrk_update", "cmdg_lsrk_steps",
     "cmdg_lsrk_steps_host", "cmdg_comm_unique_id", "cmdg_comm_init", "cmdg_exchange_begin",
     "cmdg_exchange_end", "cmdg_sync", "cmdg_kernel_launches", "cmdg_set_timing",
-    "cmdg_last_kernel_ms",
+    "cmdg_last_kernel_ms", "cmdg_set_ocean_model", "cmdg_bind_ocean_operators",
 ]
 
 
@@ -74,6 +86,8 @@ def lib():
     L.cmdg_bind_grid.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, i64,
                                  C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), i32]
     L.cmdg_bind_state.argtypes = [vp, vp, vp]
+    L.cmdg_set_ocean_model.argtypes = [vp, C.POINTER(cmdg_ocean_desc)]
+    L.cmdg_bind_ocean_operators.argtypes = [vp, vp, vp, vp]
     L.cmdg_tendency.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
     L.cmdg_lsrk_update.argtypes = [vp, vp, vp, dbl, dbl, dbl, vp]
     L.cmdg_lsrk_steps.argtypes = [vp, vp, vp, dbl, dbl, i32, C.POINTER(dbl), C.POINTER(dbl),

@@ -224,3 +224,125 @@ class AtmosModel:
                     and isinstance(bc.momentum.drag, (FreeSlip, NoSlip))
                     and isinstance(bc.energy, Insulating)):
                 raise UnsupportedModelError(f"unsupported boundary condition {bc!r}")
+
+
+# ---------------------------------------------------------------------------------------
+# Ocean: HydrostaticBoussinesqModel (src/Ocean/HydrostaticBoussinesq), OceanBC (src/Ocean/OceanBC.jl),
+# OceanGyre (src/Ocean/OceanProblems/ocean_gyre.jl), spectral filters (src/Numerics/Mesh/Filters.jl)
+# ---------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Penetrable:
+    drag: object = field(default_factory=FreeSlip)
+
+
+class KinematicStress:
+    pass
+
+
+class TemperatureFlux:
+    pass
+
+
+@dataclass(frozen=True)
+class OceanBC:
+    velocity: object = field(default_factory=lambda: Impenetrable(NoSlip()))
+    temperature: object = field(default_factory=Insulating)
+
+
+@dataclass(frozen=True)
+class OceanGyre:
+    Lˣ: float
+    Lʸ: float
+    H: float
+    τₒ: float = 1e-1
+    λʳ: float = 4 / 86400
+    θᴱ: float = 10.0
+    boundary_conditions: Tuple = (OceanBC(Impenetrable(NoSlip()), Insulating()),
+                                  OceanBC(Impenetrable(NoSlip()), Insulating()),
+                                  OceanBC(Penetrable(KinematicStress()), TemperatureFlux()))
+
+
+@dataclass
+class HydrostaticBoussinesqModel:
+    problem: OceanGyre
+    param_set: EarthParameterSet = field(default_factory=EarthParameterSet)
+    ρₒ: float = 1000.0
+    cʰ: float = 0.0
+    cᶻ: float = 0.0
+    αᵀ: float = 2e-4
+    νʰ: float = 5e3
+    νᶻ: float = 5e-3
+    κʰ: float = 1e3
+    κᶻ: float = 1e-4
+    κᶜ: float = 1e-1
+    fₒ: float = 1e-4
+    β: float = 1e-11
+    momentum_advection: Optional[object] = None   # only `nothing` (the default) is supported
+    coupling: Optional[object] = None             # Uncoupled
+    forcing: Optional[object] = None              # no forcing
+
+    def number_states(self, kind):
+        return {"Prognostic": 4, "Auxiliary": 8, "Gradient": 5, "GradientFlux": 10}[kind]
+
+    def validate(self):
+        for name in ("momentum_advection", "coupling", "forcing"):
+            if getattr(self, name) is not None:
+                raise UnsupportedModelError(f"HBModel.{name} is not supported by libcmdg")
+        if not isinstance(self.problem, OceanGyre):
+            raise UnsupportedModelError("only OceanGyre-type problems are supported")
+        for bc in self.problem.boundary_conditions:
+            ocean_bc_codes(bc)
+
+
+HBModel = HydrostaticBoussinesqModel
+
+
+def ocean_bc_codes(bc):
+    v, t = bc.velocity, bc.temperature
+    if isinstance(v, Impenetrable) and isinstance(v.drag, NoSlip):
+        vc = 1
+    elif isinstance(v, Impenetrable) and isinstance(v.drag, FreeSlip):
+        vc = 2
+    elif isinstance(v, Penetrable) and isinstance(v.drag, FreeSlip):
+        vc = 3
+    elif isinstance(v, Penetrable) and isinstance(v.drag, KinematicStress):
+        vc = 4
+    else:
+        raise UnsupportedModelError(f"unsupported ocean velocity BC {v!r}")
+    if isinstance(t, Insulating):
+        tc = 1
+    elif isinstance(t, TemperatureFlux):
+        tc = 2
+    else:
+        raise UnsupportedModelError(f"unsupported ocean temperature BC {t!r}")
+    return vc, tc
+
+
+def spectral_filter_matrix(r, Nc, σ):
+    """Filters.jl:114-131."""
+    import numpy as np
+    r = np.asarray(r, dtype=np.float64)
+    N = len(r) - 1
+    V = np.stack([np.polynomial.legendre.legval(r, [0] * n + [1]) * np.sqrt((2 * n + 1) / 2)
+                  for n in range(N + 1)], axis=1)
+    Σ = np.ones(N + 1)
+    for n in range(Nc, N + 1):
+        Σ[n] = σ((n - Nc) / (N - Nc))
+    return (V * Σ[None, :]) @ np.linalg.inv(V)
+
+
+class CutoffFilter:
+    """``CutoffFilter(grid, Nc)`` (Filters.jl:275-314); only the vertical matrix is used here."""
+
+    def __init__(self, grid, Nc):
+        self.filter_matrix = spectral_filter_matrix(grid.xi, Nc, lambda η: 0.0)
+
+
+class ExponentialFilter:
+    """``ExponentialFilter(grid, Nc, s)`` (Filters.jl:172-229)."""
+
+    def __init__(self, grid, Nc=0, s=32, α=None):
+        import numpy as np
+        α = -np.log(np.finfo(np.float64).eps) if α is None else α
+        assert s % 2 == 0
+        self.filter_matrix = spectral_filter_matrix(grid.xi, Nc, lambda η: np.exp(-α * η ** s))

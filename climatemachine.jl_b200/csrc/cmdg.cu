@@ -10,6 +10,7 @@
 //     -> update!                                         (LowStorageRungeKuttaMethod.jl:146-158)
 #include "../../include/cmdg.h"
 #include "cmdg_kernels.cuh"
+#include "cmdg_ocean.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -91,6 +92,11 @@ struct cmdg_handle_s {
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
   bool grid_bound = false;
+  // ocean (HBModel)
+  bool is_hb = false, ocean_set = false;
+  cmdg_ocean_desc od{};
+  void *Fc = nullptr, *Fe = nullptr, *Imat = nullptr, *JcV = nullptr;  // row-major operators, vgeo col 16
+  const void *vgeo_bound = nullptr;
   // communication
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -325,6 +331,104 @@ int exchange_end_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// HBModel: one evaluation in the reference's order (DGModel.jl:85-427 with the model hooks of
+// hydrostatic_boussinesq_model.jl:637-712).  Qout != nullptr fuses the RK stage update.
+// ------------------------------------------------------------------------------------
+template <class R>
+HBParams<R> make_hb_params(const cmdg_handle_s *h) {
+  const cmdg_ocean_desc &o = h->od;
+  HBParams<R> P{};
+  P.grav = (R)o.grav; P.rho0 = (R)o.rho0; P.ch = (R)o.ch; P.cz = (R)o.cz; P.alphaT = (R)o.alphaT;
+  P.nuh = (R)o.nuh; P.nuz = (R)o.nuz; P.kappah = (R)o.kappah; P.kappaz = (R)o.kappaz;
+  P.kappac = (R)o.kappac; P.f0 = (R)o.f0; P.beta = (R)o.beta;
+  P.Ly = (R)o.Ly; P.tau0 = (R)o.tau0; P.lambda_r = (R)o.lambda_r; P.thetaE = (R)o.thetaE;
+  for (int i = 0; i < 6; ++i) { P.bc_vel[i] = o.bc_velocity[i]; P.bc_temp[i] = o.bc_temperature[i]; }
+  P.nvertelem = h->d.nvertelem;
+  return P;
+}
+
+template <class R>
+int hb_launch_tend(cmdg_handle h, const HBArgs<R> &a, const HBParams<R> &P, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (h->timing) cudaEventRecord(timing_event(h), st);
+  if (h->d.nf_first == CMDG_NF_RUSANOV)
+    hb_tendency_kernel<R, 5, NF_RUSANOV><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  else
+    hb_tendency_kernel<R, 5, NF_CENTRAL><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  if (h->timing) cudaEventRecord(timing_event(h), st);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+template <class R>
+int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double beta,
+              double rkb_dt, cudaStream_t st) {
+  const bool par = h->comm && !h->nabrtorank.empty();
+  const int64_t nreal = h->d.nrealelem, nghost = h->d.nelem - nreal;
+  const int nv = h->d.nvertelem;
+  const HBParams<R> P = make_hb_params<R>(h);
+  HBArgs<R> a{};
+  a.Q = (R *)Q;
+  a.aux = (R *)h->aux;
+  a.gradflux = (R *)h->gradflux;
+  a.dQ = (R *)dQ;
+  a.Qout = (R *)Qout;
+  a.vgeoP = (const R *)h->vgeoP;
+  a.sgeoP = (const R *)h->sgeoP;
+  a.conn = h->conn;
+  a.D = (const R *)h->Ddev;
+  a.alpha = (R)alpha;
+  a.beta = (R)beta;
+  a.rkb_dt = (R)rkb_dt;
+  int rc;
+  auto grad = [&](const int *elems, int64_t n) -> int {
+    if (n <= 0) return 0;
+    HBArgs<R> g = a;
+    g.elems = elems;
+    hb_gradient_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(g, P);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+  };
+  auto column = [&](int64_t elem0, int64_t nelems, int set_wz0) -> int {
+    if (nelems <= 0) return 0;
+    hb_column_kernel<R, 5><<<(unsigned)(nelems / nv), 32, 0, st>>>(
+        (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
+        P.alphaT, nv, (int)elem0, set_wz0);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+  };
+  // update_auxiliary_state!: vertical filters on the real elements, in place
+  if (nreal > 0) {
+    hb_filter_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>((R *)Q, (const R *)h->Fc,
+                                                                       (const R *)h->Fe, (int)nreal);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  if (!par) {
+    if ((rc = grad(nullptr, nreal))) return rc;
+    if ((rc = column(0, nreal, 1))) return rc;
+    a.elems = nullptr;
+    return hb_launch_tend<R>(h, a, P, nreal, st);
+  }
+  if ((rc = exchange_begin_t<R>(h, Q, HB_S, st))) return rc;
+  if ((rc = grad(h->interior, h->ninterior))) return rc;
+  if ((rc = exchange_end_t<R>(h, Q, HB_S, st))) return rc;
+  if ((rc = grad(h->exterior, h->nexterior))) return rc;
+  if ((rc = exchange_begin_t<R>(h, h->gradflux, HB_GF, st))) return rc;
+  if ((rc = column(0, nreal, 1))) return rc;
+  a.elems = h->interior;
+  if ((rc = hb_launch_tend<R>(h, a, P, h->ninterior, st))) return rc;
+  if ((rc = exchange_end_t<R>(h, h->gradflux, HB_GF, st))) return rc;
+  if ((rc = column(nreal, nghost, 0))) return rc;
+  a.elems = h->exterior;
+  return hb_launch_tend<R>(h, a, P, h->nexterior, st);
+}
+
 template <class R>
 TendArgs<R> base_args(cmdg_handle h) {
   TendArgs<R> a{};
@@ -345,6 +449,7 @@ TendArgs<R> base_args(cmdg_handle h) {
 template <class R>
 int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double beta,
                cudaStream_t st) {
+  if (h->is_hb) return hb_eval_t<R>(h, dQ, Q, nullptr, alpha, beta, 0.0, st);
   const bool par = h->comm && !h->nabrtorank.empty();
   const int64_t nreal = h->d.nrealelem;
   TendArgs<R> a = base_args<R>(h);
@@ -406,7 +511,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   const size_t bytes = (size_t)h->d.nelem * h->d.nstate * h->Np * sizeof(R);
   if (!h->Qtmp) CU(cudaMalloc(&h->Qtmp, bytes));
   R *cur = (R *)Q, *nxt = (R *)h->Qtmp;
-  if (par) {
+  if (par && !h->is_hb) {
     // ghosts of the initial state
     int rc;
     if ((rc = exchange_begin_t<R>(h, cur, h->d.nstate, st))) return rc;
@@ -416,6 +521,16 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   for (int64_t step = 0; step < nsteps; ++step) {
     const double time = t0 + (double)step * dt;
     for (int s = 0; s < nstage; ++s) {
+      if (h->is_hb) {
+        int rc = hb_eval_t<R>(h, dQ, cur, nxt, 1.0, rka[s], (double)((R)rkb[s] * (R)dt), st);
+        if (rc) return rc;
+        // the vertical filters act on the stage state itself: the ghost layer of the new state is
+        // refreshed by the next evaluation's exchange
+        R *tmp2 = cur;
+        cur = nxt;
+        nxt = tmp2;
+        continue;
+      }
       TendArgs<R> a = base_args<R>(h);
       a.Q = cur;
       a.dQ = (R *)dQ;
@@ -582,6 +697,16 @@ int bind_grid_t(cmdg_handle h, const void *vgeo, const void *sgeo, const void *D
   return 0;
 }
 
+template <class R>
+int upload_rowmajor(cmdg_handle h, void **dst, const void *src_dev, int n) {
+  std::vector<R> a(n * n), b(n * n);
+  CU(cudaMemcpy(a.data(), src_dev, a.size() * sizeof(R), cudaMemcpyDeviceToHost));
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) b[r * n + c] = a[r + n * c];
+  if (!*dst) CU(cudaMalloc(dst, b.size() * sizeof(R)));
+  CU(cudaMemcpy(*dst, b.data(), b.size() * sizeof(R), cudaMemcpyHostToDevice));
+  return 0;
+}
 #define DISPATCH_FT(h, expr64, expr32) ((h)->d.float_bytes == CMDG_F64 ? (expr64) : (expr32))
 
 }  // namespace
@@ -606,9 +731,42 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (d->dim != 3) return fail(nullptr, CMDG_ERR_UNSUPPORTED, "only dim = 3 is supported");
   if (d->N != 4)
     return fail(nullptr, CMDG_ERR_UNSUPPORTED, "only polynomial order N = 4 is compiled in");
-  if (d->model != CMDG_MODEL_ATMOS_DRY)
+  if (d->model != CMDG_MODEL_ATMOS_DRY && d->model != CMDG_MODEL_HB)
     return fail(nullptr, CMDG_ERR_UNSUPPORTED,
-                "unsupported balance law (only the dry AtmosModel is compiled in)");
+                "unsupported balance law (only the dry AtmosModel and the ocean HBModel are compiled in)");
+  if (d->model == CMDG_MODEL_HB) {
+    if (d->nf_first != CMDG_NF_RUSANOV && d->nf_first != CMDG_NF_CENTRAL)
+      return fail(nullptr, CMDG_ERR_UNSUPPORTED, "HBModel supports Rusanov / Central first-order fluxes");
+    if (d->nf_second != CMDG_NF_CENTRAL || d->nf_gradient != CMDG_NF_CENTRAL)
+      return fail(nullptr, CMDG_ERR_UNSUPPORTED, "second-order / gradient fluxes must be Central");
+    if (d->nstate != 4 || d->naux != 8 || d->ngrad != 5 || d->ngradflux != 10)
+      return fail(nullptr, CMDG_ERR_INVALID, "HBModel state sizes are 4 / 8 / 5 / 10");
+    if (d->nvertelem <= 0 || d->nrealelem % d->nvertelem != 0 || d->nelem % d->nvertelem != 0)
+      return fail(nullptr, CMDG_ERR_INVALID, "HBModel needs a stacked topology (nvertelem > 0)");
+    if (d->diffusion_direction != CMDG_DIR_EVERY)
+      return fail(nullptr, CMDG_ERR_UNSUPPORTED, "HBModel: diffusion_direction must be EveryDirection");
+    if (d->nrealelem < 0 || d->nelem < d->nrealelem || d->nelem > 0x7fffffffLL)
+      return fail(nullptr, CMDG_ERR_INVALID, "bad element counts");
+    int ndev0 = 0;
+    if (cudaGetDeviceCount(&ndev0) != cudaSuccess || ndev0 == 0)
+      return fail(nullptr, CMDG_ERR_NODEVICE, "no CUDA device available (libcmdg has no CPU fallback)");
+    h = new cmdg_handle_s();
+    h->d = *d;
+    h->Nq = d->N + 1;
+    h->Np = h->Nq * h->Nq * h->Nq;
+    h->Nfp = h->Nq * h->Nq;
+    h->fb = d->float_bytes;
+    h->is_hb = true;
+    h->visc = true;
+    if (cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
+    }
+    *out = h;
+    return CMDG_OK;
+  }
   if (d->nf_first < CMDG_NF_RUSANOV || d->nf_first > CMDG_NF_ROE)
     return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported first-order numerical flux");
   if (d->nf_second != CMDG_NF_CENTRAL || d->nf_gradient != CMDG_NF_CENTRAL)
@@ -665,7 +823,8 @@ int cmdg_destroy(cmdg_handle h) {
   if (!h) return CMDG_OK;
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
-                  h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev};
+                  h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
+                  h->Fc, h->Fe, h->Imat, h->JcV};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -686,6 +845,8 @@ int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int6
                    const int64_t *nabrtovmaprecv, int32_t nnabr) {
   if (!h) return CMDG_ERR_INVALID;
   if (h->grid_bound) return fail(h, CMDG_ERR_INVALID, "grid already bound");
+  if (h->is_hb && !h->ocean_set)
+    return fail(h, CMDG_ERR_INVALID, "call cmdg_set_ocean_model before cmdg_bind_grid");
   if (!vgeo || !sgeo || !vmapM || !vmapP || !elemtobndy || !D)
     return fail(h, CMDG_ERR_INVALID, "null grid array");
   if (ninterior + nexterior != h->d.nrealelem)
@@ -708,7 +869,53 @@ int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int6
     h->recvrange.push_back(nabrtovmaprecv[2 * n] - 1);
     h->recvrange.push_back(nabrtovmaprecv[2 * n + 1]);
   }
+  if (h->is_hb) {
+    const size_t n = (size_t)h->d.nelem * h->Np;
+    CU(cudaMalloc(&h->JcV, n * h->fb + 16));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (h->d.float_bytes == CMDG_F64)
+      extract_column_kernel<double><<<nb, 256>>>((double *)h->JcV, (const double *)vgeo, h->Np, 25, 15, h->d.nelem);
+    else
+      extract_column_kernel<float><<<nb, 256>>>((float *)h->JcV, (const float *)vgeo, h->Np, 25, 15, h->d.nelem);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    h->launches++;
+  }
   h->grid_bound = true;
+  return CMDG_OK;
+}
+
+int cmdg_set_ocean_model(cmdg_handle h, const cmdg_ocean_desc *o) {
+  if (!h || !o) return CMDG_ERR_INVALID;
+  if (!h->is_hb) return fail(h, CMDG_ERR_INVALID, "handle was not created with CMDG_MODEL_HB");
+  if (o->struct_bytes != (int32_t)sizeof(cmdg_ocean_desc))
+    return fail(h, CMDG_ERR_INVALID, "cmdg_ocean_desc size mismatch (ABI)");
+  if (o->nbc < 0 || o->nbc > 6) return fail(h, CMDG_ERR_INVALID, "nbc must be 0..6");
+  for (int i = 0; i < o->nbc; ++i) {
+    if (o->bc_velocity[i] < CMDG_OCEAN_VEL_NOSLIP || o->bc_velocity[i] > CMDG_OCEAN_VEL_PENETRABLE_KINEMATIC_STRESS)
+      return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported ocean velocity boundary condition");
+    if (o->bc_temperature[i] != CMDG_OCEAN_TEMP_INSULATING && o->bc_temperature[i] != CMDG_OCEAN_TEMP_FLUX)
+      return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported ocean temperature boundary condition");
+  }
+  h->od = *o;
+  h->d.nbc = o->nbc;
+  h->ocean_set = true;
+  return CMDG_OK;
+}
+
+int cmdg_bind_ocean_operators(cmdg_handle h, const void *Fc, const void *Fe, const void *Imat) {
+  if (!h || !Fc || !Fe || !Imat) return CMDG_ERR_INVALID;
+  if (!h->is_hb) return fail(h, CMDG_ERR_INVALID, "handle was not created with CMDG_MODEL_HB");
+  int rc;
+  if (h->d.float_bytes == CMDG_F64) {
+    if ((rc = upload_rowmajor<double>(h, &h->Fc, Fc, h->Nq))) return rc;
+    if ((rc = upload_rowmajor<double>(h, &h->Fe, Fe, h->Nq))) return rc;
+    if ((rc = upload_rowmajor<double>(h, &h->Imat, Imat, h->Nq))) return rc;
+  } else {
+    if ((rc = upload_rowmajor<float>(h, &h->Fc, Fc, h->Nq))) return rc;
+    if ((rc = upload_rowmajor<float>(h, &h->Fe, Fe, h->Nq))) return rc;
+    if ((rc = upload_rowmajor<float>(h, &h->Imat, Imat, h->Nq))) return rc;
+  }
   return CMDG_OK;
 }
 
@@ -725,6 +932,8 @@ int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
 static int check_ready(cmdg_handle h) {
   if (!h) return CMDG_ERR_INVALID;
   if (!h->grid_bound || !h->aux) return fail(h, CMDG_ERR_INVALID, "bind the grid and the state first");
+  if (h->is_hb && (!h->Fc || !h->Imat))
+    return fail(h, CMDG_ERR_INVALID, "HBModel: call cmdg_bind_ocean_operators first");
   return 0;
 }
 

@@ -30,7 +30,7 @@ class DiscontinuousSpectralElementGrid:
     def __init__(self, N, vgeo, sgeo, vmapM, vmapP, elemtobndy, D, nrealelem,
                  interiorelems=None, exteriorelems=None, vmapsend=None, vmaprecv=None,
                  nabrtorank=(), nabrtovmapsend=(), nabrtovmaprecv=(), nvertelem=0,
-                 device="cuda"):
+                 device="cuda", Imat=None, xi=None):
         dev = torch.device(device)
         self.N = int(N)
         self.Nq = self.N + 1
@@ -62,6 +62,9 @@ class DiscontinuousSpectralElementGrid:
         self.nabrtovmaprecv = [(int(a), int(b)) for a, b in nabrtovmaprecv]
         self.nvertelem = int(nvertelem)
         self.device = dev
+        # grid.Imat[end] (Julia memory order) and the 1-D reference points, used by the ocean model
+        self.Imat = None if Imat is None else tt(np.asarray(Imat).T.copy()).to(self.FT)
+        self.xi = None if xi is None else np.asarray(xi, dtype=np.float64)
 
 
 class MPIStateArray:
@@ -109,7 +112,12 @@ class DGModel:
                  numerical_flux_second_order, numerical_flux_gradient,
                  state_auxiliary=None, state_gradient_flux=None,
                  direction=None, diffusion_direction=None,
-                 skip_zero_viscosity=False, write_aux_diagnostics=True):
+                 skip_zero_viscosity=False, write_aux_diagnostics=True, modeldata=None):
+        if isinstance(balance_law, bl.HydrostaticBoussinesqModel):
+            self._init_ocean(balance_law, grid, numerical_flux_first_order,
+                             numerical_flux_second_order, numerical_flux_gradient,
+                             state_auxiliary, state_gradient_flux, modeldata)
+            return
         if not isinstance(balance_law, bl.AtmosModel):
             raise bl.UnsupportedModelError(
                 f"balance law {type(balance_law).__name__} is not compiled into libcmdg")
@@ -185,6 +193,66 @@ class DGModel:
             _ptr(g.D), _ptr(g.interiorelems), g.interiorelems.numel(), _ptr(g.exteriorelems),
             g.exteriorelems.numel(), _ptr(g.vmapsend), g.vmapsend.numel(), _ptr(g.vmaprecv),
             g.vmaprecv.numel(), ranks, sr, rr, nn), self._h)
+        _lib.check(L.cmdg_bind_state(self._h, _ptr(self.state_auxiliary.data),
+                                     _ptr(self.state_gradient_flux.data)), self._h)
+
+    def _init_ocean(self, m, grid, nf1, nf2, nfg, state_auxiliary, state_gradient_flux, modeldata):
+        m.validate()
+        if type(nf1) not in (bl.RusanovNumericalFlux, bl.CentralNumericalFluxFirstOrder):
+            raise bl.UnsupportedModelError("HBModel supports Rusanov / Central first-order fluxes")
+        if not isinstance(nf2, bl.CentralNumericalFluxSecondOrder) or \
+                not isinstance(nfg, bl.CentralNumericalFluxGradient):
+            raise bl.UnsupportedModelError("second-order/gradient fluxes must be Central")
+        if modeldata is None or "vert_filter" not in modeldata or "exp_filter" not in modeldata:
+            raise ValueError("HBModel needs modeldata = dict(vert_filter=..., exp_filter=...)")
+        if grid.Imat is None:
+            raise ValueError("the grid has no Imat (stack-integral operator)")
+        self.balance_law, self.grid = m, grid
+        self.numerical_flux_first_order = nf1
+        self.diffusion_direction = bl.EveryDirection()
+        self.modeldata = modeldata
+        self.state_auxiliary = state_auxiliary or MPIStateArray(grid, 8)
+        self.state_gradient_flux = state_gradient_flux or MPIStateArray(grid, 10)
+        L = _lib.lib()
+        d = _lib.cmdg_desc()
+        d.struct_bytes = C.sizeof(_lib.cmdg_desc)
+        d.float_bytes = 8 if grid.FT == torch.float64 else 4
+        d.dim, d.N = 3, grid.N
+        d.nelem, d.nrealelem, d.nvertelem = grid.nelem, grid.nrealelem, grid.nvertelem
+        d.model = _lib.MODEL_HB
+        d.nf_first = _NF1[type(nf1)]
+        d.nf_second = d.nf_gradient = _lib.NF_CENTRAL
+        d.nstate, d.naux, d.ngrad, d.ngradflux = 4, 8, 5, 10
+        self._desc = d
+        self._h = C.c_void_p()
+        _lib.check(L.cmdg_create(C.byref(d), C.byref(self._h)))
+        o = _lib.cmdg_ocean_desc()
+        o.struct_bytes = C.sizeof(_lib.cmdg_ocean_desc)
+        bcs = m.problem.boundary_conditions
+        o.nbc = len(bcs)
+        for i, bc in enumerate(bcs):
+            o.bc_velocity[i], o.bc_temperature[i] = bl.ocean_bc_codes(bc)
+        p = m.problem
+        o.grav, o.rho0, o.ch, o.cz, o.alphaT = m.param_set.grav, m.ρₒ, m.cʰ, m.cᶻ, m.αᵀ
+        o.nuh, o.nuz, o.kappah, o.kappaz, o.kappac = m.νʰ, m.νᶻ, m.κʰ, m.κᶻ, m.κᶜ
+        o.f0, o.beta = m.fₒ, m.β
+        o.Lx, o.Ly, o.H, o.tau0, o.lambda_r, o.thetaE = p.Lˣ, p.Lʸ, p.H, p.τₒ, p.λʳ, p.θᴱ
+        _lib.check(L.cmdg_set_ocean_model(self._h, C.byref(o)), self._h)
+        g = grid
+        nn = len(g.nabrtorank)
+        ranks = (C.c_int32 * max(nn, 1))(*g.nabrtorank)
+        sr = (C.c_int64 * max(2 * nn, 1))(*[v for ab in g.nabrtovmapsend for v in ab])
+        rr = (C.c_int64 * max(2 * nn, 1))(*[v for ab in g.nabrtovmaprecv for v in ab])
+        _lib.check(L.cmdg_bind_grid(
+            self._h, _ptr(g.vgeo), _ptr(g.sgeo), _ptr(g.vmapM), _ptr(g.vmapP), _ptr(g.elemtobndy),
+            _ptr(g.D), _ptr(g.interiorelems), g.interiorelems.numel(), _ptr(g.exteriorelems),
+            g.exteriorelems.numel(), _ptr(g.vmapsend), g.vmapsend.numel(), _ptr(g.vmaprecv),
+            g.vmaprecv.numel(), ranks, sr, rr, nn), self._h)
+        # filter matrices / Imat as device arrays in Julia (column-major) memory order
+        dev = grid.device
+        self._Fc = torch.as_tensor(np.ascontiguousarray(modeldata["vert_filter"].filter_matrix.T)).to(dev).to(grid.FT)
+        self._Fe = torch.as_tensor(np.ascontiguousarray(modeldata["exp_filter"].filter_matrix.T)).to(dev).to(grid.FT)
+        _lib.check(L.cmdg_bind_ocean_operators(self._h, _ptr(self._Fc), _ptr(self._Fe), _ptr(g.Imat)), self._h)
         _lib.check(L.cmdg_bind_state(self._h, _ptr(self.state_auxiliary.data),
                                      _ptr(self.state_gradient_flux.data)), self._h)
 

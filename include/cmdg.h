@@ -102,6 +102,25 @@ typedef struct {
   double R_d, cp_d, cv_d, T_0, MSLP, grav, Omega, inv_Pr_turb;
 } cmdg_desc;
 
+/*
+ * Ocean HydrostaticBoussinesqModel (src/Ocean/HydrostaticBoussinesq/hydrostatic_boussinesq_model.jl:40-103)
+ * with an AbstractSimpleBoxProblem of the OceanGyre family (src/Ocean/OceanProblems/ocean_gyre.jl):
+ * model constants, the surface forcing used by the flux-based boundary conditions, and one
+ * OceanBC (src/Ocean/OceanBC.jl) per boundary tag.  Used with cmdg_desc.model = CMDG_MODEL_HB
+ * (nstate 4, naux 8, ngrad 5, ngradflux 10; the Atmos-only fields of cmdg_desc are ignored).
+ */
+enum { CMDG_OCEAN_VEL_NOSLIP = 1, CMDG_OCEAN_VEL_FREESLIP = 2, CMDG_OCEAN_VEL_PENETRABLE_FREESLIP = 3,
+       CMDG_OCEAN_VEL_PENETRABLE_KINEMATIC_STRESS = 4 };
+enum { CMDG_OCEAN_TEMP_INSULATING = 1, CMDG_OCEAN_TEMP_FLUX = 2 };
+typedef struct {
+  int32_t struct_bytes;
+  int32_t nbc;
+  int32_t bc_velocity[6];     /* CMDG_OCEAN_VEL_*  for elemtobndy tag 1..nbc */
+  int32_t bc_temperature[6];  /* CMDG_OCEAN_TEMP_* */
+  double grav, rho0, ch, cz, alphaT, nuh, nuz, kappah, kappaz, kappac, f0, beta;
+  double Lx, Ly, H, tau0, lambda_r, thetaE;
+} cmdg_ocean_desc;
+
 /* library version (CMDG_VERSION) */
 int cmdg_version(void);
 
@@ -135,6 +154,18 @@ int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int6
                    int64_t nvmapsend, const int64_t *vmaprecv, int64_t nvmaprecv,
                    const int32_t *nabrtorank_host, const int64_t *nabrtovmapsend_host,
                    const int64_t *nabrtovmaprecv_host, int32_t nnabr);
+
+/*
+ * HBModel only.  cmdg_set_ocean_model: the model/problem constants (call before the first
+ * tendency).  cmdg_bind_ocean_operators: the two vertical filter matrices that
+ * update_auxiliary_state! applies in every evaluation (hydrostatic_boussinesq_model.jl:637-663;
+ * `modeldata.vert_filter.filter_matrices[end]`, `modeldata.exp_filter.filter_matrices[end]`,
+ * Nq x Nq, Julia layout) and grid.Imat[end] used by the stack integrals
+ * (src/Numerics/Mesh/Grids.jl:1184-1206), all device pointers.
+ */
+int cmdg_set_ocean_model(cmdg_handle h, const cmdg_ocean_desc *ocean);
+int cmdg_bind_ocean_operators(cmdg_handle h, const void *vert_filter_matrix,
+                              const void *exp_filter_matrix, const void *Imat);
 
 /*
  * Binds dg.state_auxiliary.data (Np x naux x nelem) and dg.state_gradient_flux.data

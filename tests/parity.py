@@ -253,3 +253,91 @@ def box_case(nf="rusanov", nsteps=1, dt=0.01, turbulence=("smagorinsky", 0.21),
     Q0 = bubble_state(model, g, aux)
     return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
                         diffusion_direction=diffusion_direction)
+
+
+# ---------------------------------------------------------------------------------------
+# ocean HBModel
+# ---------------------------------------------------------------------------------------
+def ocean_setup(csize=1, nelem=(5, 5, 5)):
+    from tests.test_oracle_ocean import gyre_setup
+    return gyre_setup(csize, nelem)
+
+
+def device_ocean_dg(omodel, g, odgm, nf="rusanov", rank=0):
+    P = pkg()
+    dgrid = P.DiscontinuousSpectralElementGrid(
+        g.N[0], g.vgeo, g.sgeo, g.vmapM, g.vmapP, g.elemtobndy, g.D[0], g.nreal,
+        interiorelems=g.interiorelems, exteriorelems=g.exteriorelems,
+        vmapsend=g.vmapsend, vmaprecv=g.vmaprecv, nabrtorank=g.nabrtorank,
+        nabrtovmapsend=g.nabrtovmapsend, nabrtovmaprecv=g.nabrtovmaprecv,
+        nvertelem=g.topology.stacksize, Imat=g.Imat[2], xi=g.xi[2])
+    pr = omodel.problem
+    m = P.HBModel(P.OceanGyre(pr.Lx, pr.Ly, pr.H), cʰ=float(omodel.ch))
+    aux = P.MPIStateArray(dgrid, 8, data=odgm.state_auxiliary[rank].data)
+    md = dict(vert_filter=P.CutoffFilter(dgrid, 3), exp_filter=P.ExponentialFilter(dgrid, 1, 8))
+    dg = P.DGModel(m, dgrid, getattr(P, NF[nf])(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, modeldata=md)
+    return dg, dgrid
+
+
+def ocean_case(nsteps=2, dt=120.0, nelem=(5, 5, 5), spinup=3, nf="rusanov"):
+    """HBModel: one evaluation (filters + gradient pass + column integrals + tendency) and
+    LSRK144 steps, oracle vs libcmdg; the state is first spun up by the oracle so that every
+    term (advection by w, pressure, wind stress, convective adjustment) is active."""
+    from oracle import ocean as oocean
+    P = pkg()
+    model, gs, prob = ocean_setup(1, nelem)
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], nf)
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=dt, t0=0.0)
+    if spinup:
+        oode.solve(oQ, osol, numberofsteps=spinup)
+    dg, dgrid = device_ocean_dg(model, g, odgm, nf)
+    dQ = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    odQ = [oQ[0].similar()]
+    odgm(odQ, oQ, 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 4)
+    dT.data.fill_(float("nan"))
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    res = {
+        "tendency_rel_l2": rel_l2(dT.realdata.cpu().numpy(), odQ[0].realdata),
+        "filtered_state_rel_l2": rel_l2(dQ.realdata.cpu().numpy(), oQ[0].realdata),
+        "gradflux_rel_l2": rel_l2(dg.state_gradient_flux.realdata.cpu().numpy(),
+                                  odgm.state_gradient_flux[0].realdata),
+        "aux_rel_l2": rel_l2(dg.state_auxiliary.realdata[:, 1:4].cpu().numpy(),
+                             odgm.state_auxiliary[0].realdata[:, 1:4]),
+    }
+    osol2 = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=dt, t0=0.0)
+    oode.solve(oQ, osol2, numberofsteps=nsteps)
+    dsol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=dt, t0=0.0)
+    P.solve(dQ, dsol, numberofsteps=nsteps)
+    res["state_rel_l2"] = rel_l2(dQ.realdata.cpu().numpy(), oQ[0].realdata)
+    res["launches"] = dg.kernel_launches()
+    dg.close()
+    return res
+
+
+def ocean_refvals_on_device():
+    """test_ocean_gyre_short.jl run entirely through libcmdg: min/max/mean/std after 1 h."""
+    from oracle import ocean as oocean
+    P = pkg()
+    model, gs, prob = ocean_setup(1, (5, 5, 5))
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], "rusanov")
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    dg, dgrid = device_ocean_dg(model, g, odgm)
+    dQ = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    sol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=120.0, t0=0.0)
+    P.solve(dQ, sol, numberofsteps=30)
+
+    class Wrap:
+        def __init__(self, t, nreal):
+            self.realdata = t.cpu().numpy()[:nreal]
+    out = {}
+    for name, arr in (("Q", dQ), ("aux", dg.state_auxiliary)):
+        w = Wrap(arr.data, g.nreal)
+        for ivar in range(4):
+            out[(name, ivar)] = oocean.statecheck(w, ivar)
+    dg.close()
+    return out

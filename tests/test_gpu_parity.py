@@ -128,3 +128,25 @@ def test_experimental_pipelined_kernel_matches(monkeypatch):
     res = parity.vortex_case(nelem=(4, 4, 2), nf="central", nsteps=2)
     assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
     assert res["state_rel_l2"] <= 1e-13, res
+
+
+def test_ocean_hbmodel_tendency_and_steps():
+    """HBModel (config 5 physics): in-tendency vertical filters, gradient pass with the
+    convective-adjustment switch, column integrals, flux-based ocean BCs, LSRK144."""
+    res = parity.ocean_case(nsteps=2)
+    assert res["filtered_state_rel_l2"] <= 1e-14, res
+    assert res["gradflux_rel_l2"] <= 1e-12, res
+    assert res["aux_rel_l2"] <= 1e-12, res
+    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
+    assert res["state_rel_l2"] <= 1e-12, res
+
+
+def test_ocean_gyre_reference_values_on_device():
+    """The reference's own regression values (test/Ocean/refvals/test_ocean_gyre_refvals.jl,
+    `short`) reproduced by the CUDA path: 5x5x5 elements, 30 LSRK144 steps of 120 s."""
+    from tests.test_oracle_ocean import REF_SHORT, DIGITS, close_digits
+    got = parity.ocean_refvals_on_device()
+    for key, ref in REF_SHORT.items():
+        digs = DIGITS.get(key, (12, 12, 12, 12))
+        for gval, r, d in zip(got[key], ref, digs):
+            assert close_digits(gval, r, d - 2), (key, got[key], ref)
