@@ -94,7 +94,43 @@ def main():
     Q0s = [oatmos.init_baroclinic_wave(model, np.moveaxis(a.data[:g.nreal], 1, 0))
            for g, a in zip(gs, tmp.state_auxiliary)]
     run_case("held_suarez_like", model, gs, Q0s, "rusanov", 0.5, 2, rank, world, False, "horizontal")
+    run_ocean(rank, world)
     dist.destroy_process_group()
+
+
+def run_ocean(rank, world):
+    """HBModel on a partitioned box: Q and gradient-flux exchanges, ghost column integrals."""
+    P = parity.pkg()
+    model, gs, prob = parity.ocean_setup(world, (4, 4, 3))
+    odgm = odg.DGModel(model, gs, "rusanov")
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=120.0)
+    oode.solve(oQ, osol, numberofsteps=2)       # spin-up so that every term is active
+    g = gs[rank]
+    dg, dgrid = parity.device_ocean_dg(model, g, odgm, rank=rank)
+    uid = [P.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    dg.comm_init(uid[0], rank, world)
+    data = oQ[rank].data.copy()
+    data[g.nreal:] = np.nan
+    dQ = P.MPIStateArray(dgrid, 4, data=data)
+    odQ = [q.similar() for q in oQ]
+    odgm(odQ, oQ, 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 4)
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    r1 = parity.rel_l2(dT.realdata.cpu().numpy(), odQ[rank].realdata)
+    osol2 = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=120.0)
+    oode.solve(oQ, osol2, numberofsteps=2)
+    dsol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=120.0)
+    P.solve(dQ, dsol, numberofsteps=2)
+    r2 = parity.rel_l2(dQ.realdata.cpu().numpy(), oQ[rank].realdata)
+    res = torch.tensor([r1, r2], dtype=torch.float64, device="cuda")
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY ocean_hb world={world} tendency_rel_l2={float(res[0]):.3e} "
+              f"state_rel_l2={float(res[1]):.3e}", flush=True)
+    assert float(res[0]) <= 1e-12 and float(res[1]) <= 1e-12, res
+    dg.close()
 
 
 if __name__ == "__main__":

@@ -115,7 +115,7 @@ def test_multi_gpu_halo_and_parity():
          os.path.join(root, "tests", "multi_gpu_parity.py")],
         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MULTI_GPU_PARITY") == 3
+    assert out.stdout.count("MULTI_GPU_PARITY") == 4
 
 
 def test_experimental_pipelined_kernel_matches(monkeypatch):
