@@ -34,6 +34,14 @@ def algorithmic_bytes_per_node(workload):
     """compulsory bytes per node of one fused tendency+stage launch
     (Float64).  Stage 1 of every step has beta = RKA[1] = 0 and does not read dQ."""
     w = 8
+    if workload == "ocean_gyre":
+        # HBModel (S = 4, A_vol = y,w,pkin,wz0, A_face = w,pkin, 9 gradient-flux columns read by
+        # the tendency kernel on both sides), LSRK144: 14 stages, stage 1 skips the dQ read.
+        # Whole evaluation incl. gradient pass (262.4), column integrals (40), filters (48): 872.4.
+        S, A_vol, A_face, GFu = 4, 4, 2, 9
+        b_eval = w * (3 * S + 11 + A_vol) + 1.2 * (w * (5 + S + A_face) + 8) + w * GFu + 1.2 * w * GFu
+        b_stage = b_eval + w * S
+        return b_eval, (13 * b_stage + (b_stage - w * S)) / 14
     if workload == "baroclinic_wave":
         S, A_vol, A_face = 5, 6, 2
     else:  # isentropic vortex, Euler-minimal
@@ -120,6 +128,20 @@ def build_case(P, workload, ne, nvert, rank, nranks, device):
                              source=(P.Gravity(), P.Coriolis()),
                              boundaryconditions=(P.AtmosBC(), P.AtmosBC()))
         dt = 0.4     # s; vertical acoustic CFL ~0.3
+    elif workload == "ocean_gyre":
+        # BASELINE.json configs[4]: OceanBoxGCM HBModel, 20 x 20 x 50 elements per GPU
+        # (experiments/OceanBoxGCM/homogeneous_box.jl:11-21), box widened in x with the GPU count
+        nx = ne * nranks
+        prob = P.OceanGyre(4e6 * nranks, 4e6, 1000.0)
+        br = (np.linspace(0, prob.Lˣ, nx + 1), np.linspace(0, prob.Lʸ, ne + 1), np.linspace(-prob.H, 0, nvert + 1))
+        topo = tp.stacked_brick_topology(br, (False, False, False), ((1, 1), (1, 1), (2, 3)), rank, nranks)
+        grid = gr.build_grid(topo, 4, torch.float64, None, device)
+        model = P.HBModel(prob, cʰ=float(np.sqrt(9.81 * prob.H)))
+        Q0, aux = ai.ocean_gyre_state(prob, grid)
+        md = dict(vert_filter=P.CutoffFilter(grid, 3), exp_filter=P.ExponentialFilter(grid, 1, 8))
+        dg = P.DGModel(model, grid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                       P.CentralNumericalFluxGradient(), state_auxiliary=aux, modeldata=md)
+        return dict(topo=topo, grid=grid, model=model, dg=dg, aux=aux, dt=55.0, ai=ai, Q0=Q0)
     else:
         L = 0.05
         br = tuple(np.linspace(-L, L, ne + 1) for _ in range(3))
@@ -148,8 +170,15 @@ def run_b200(args):
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    ne = args.ne or (WEAK_NE.get(world, int(round(32 * world ** 0.5))) if args.workload == "baroclinic_wave"
-                     else int(round(64 * world ** (1 / 3))))
+    ocean = args.workload == "ocean_gyre"
+    NSTATE, NSTAGE = (4, 14) if ocean else (5, 5)
+    if ocean:
+        ne = args.ne or 20
+        if args.nvert == 10:
+            args.nvert = 50
+    else:
+        ne = args.ne or (WEAK_NE.get(world, int(round(32 * world ** 0.5))) if args.workload == "baroclinic_wave"
+                         else int(round(64 * world ** (1 / 3))))
     case = build_case(P, args.workload, ne, args.nvert, rank, world, dev)
     dg, grid, model, ai = case["dg"], case["grid"], case["model"], case["ai"]
     if world > 1:
@@ -157,15 +186,21 @@ def run_b200(args):
         dist.broadcast_object_list(uid, src=0)
         dg.comm_init(uid[0], rank, world)
     # auxiliary state and initial condition (setup; harness-side, torch on the device)
-    ex = (lambda arr: dg.ghost_exchange(arr)) if world > 1 else None
-    aux0 = ai.init_state_auxiliary(model, grid, exchange=ex)
-    case["aux"].data.copy_(aux0.data)
     Q = P.MPIStateArray(grid, NSTATE)
-    if args.workload == "baroclinic_wave":
-        Q.data[:grid.nrealelem] = ai.baroclinic_wave(model, grid, case["aux"])
+    if ocean:
+        Q.data[:grid.nrealelem] = case["Q0"]
+        if world > 1:
+            dg.ghost_exchange(case["aux"])
+        sol = P.LSRK144NiegemannDiehlBusch(dg, Q, dt=case["dt"], t0=0.0)
     else:
-        Q.data[:grid.nrealelem] = ai.isentropic_vortex(model, grid, 0.0)
-    sol = P.LSRK54CarpenterKennedy(dg, Q, dt=case["dt"], t0=0.0)
+        ex = (lambda arr: dg.ghost_exchange(arr)) if world > 1 else None
+        aux0 = ai.init_state_auxiliary(model, grid, exchange=ex)
+        case["aux"].data.copy_(aux0.data)
+        if args.workload == "baroclinic_wave":
+            Q.data[:grid.nrealelem] = ai.baroclinic_wave(model, grid, case["aux"])
+        else:
+            Q.data[:grid.nrealelem] = ai.isentropic_vortex(model, grid, 0.0)
+        sol = P.LSRK54CarpenterKennedy(dg, Q, dt=case["dt"], t0=0.0)
     nreal = grid.nrealelem
     nodes_local = nreal * NP
 
@@ -231,7 +266,7 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    evals = 5 * args.steps
+    evals = NSTAGE * args.steps
     dof = nodes * NSTATE
     value = dof * evals / (ms * 1e-3) / 1e9
     b_eval, b_launch_node = algorithmic_bytes_per_node(args.workload)
@@ -263,16 +298,19 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": (f"dry baroclinic wave, cubed sphere ne={ne} x {args.nvert} vertical, N=4, "
                                 "Rusanov, LSRK54, dt=0.4 s" if args.workload == "baroclinic_wave"
+                                else f"OceanBoxGCM HBModel ocean gyre, {ne * world}x{ne}x{args.nvert} elements, N=4, "
+                                "Rusanov, LSRK144 (a step = 14 stages), dt=55 s" if ocean
                                 else f"isentropic vortex, periodic box {ne}^3, N=4, Rusanov, LSRK54"),
                    "nelem_total": int(nodes / NP), "dof_total": int(dof),
-                   "cache": "inputs larger than L2 (state %.0f MB per GPU vs 126 MB L2)" % (nodes_local * 40 / 1e6),
-                   "skip_zero_viscosity": True, "parallelism": f"element partition x{world}"},
+                   "cache": "inputs larger than L2 (Q+dQ+Qout+aux+geometry = %.0f MB per GPU vs 126 MB L2)"
+                            % (nodes_local * 8 * (3 * NSTATE + case["aux"].nstate + 10 + 4.8 + (10 if ocean else 0)) / 1e6),
+                   "skip_zero_viscosity": not ocean, "parallelism": f"element partition x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "dg_tendency_kernel<double,5,RUSANOV,...>",
+                     "kernel": "hb_tendency_kernel<double,5,RUSANOV>" if ocean else "dg_tendency_kernel<double,5,RUSANOV,...>",
                      "algorithmic_bytes_per_node_per_launch": b_launch_node,
                      "kernel_ms_per_stage": stage_ms, "launches_per_stage": launches_per_stage},
-        "e2e": {"value": dof * 5 * e2e_steps / e2e_s / 1e9, "unit": "GDOF/s",
+        "e2e": {"value": dof * NSTAGE * e2e_steps / e2e_s / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": int(nodes_local * NSTATE * 8),
                 "d2h_bytes_per_step": int(nodes_local * NSTATE * 8),
                 "api": "cmdg_lsrk_steps_host (pinned host state in/out every step)",
@@ -281,7 +319,7 @@ def run_b200(args):
         "clocks": clk,
         "norm_ratio": norm1 / norm0,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not ocean:
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -384,7 +422,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex"])
+    ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex", "ocean_gyre"])
     ap.add_argument("--ne", type=int, default=0, help="horizontal elements per cube edge / box edge")
     ap.add_argument("--nvert", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

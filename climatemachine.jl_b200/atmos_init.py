@@ -220,3 +220,15 @@ def baroclinic_wave(model, grid, aux):
     e_kin = 0.5 * (uc[0] ** 2 + uc[1] ** 2 + uc[2] ** 2)
     e_tot = e_kin + a[:, lay["Φ"]] + p.cv_d * (T_v - p.T_0)
     return torch.stack([ρ, ρ * uc[0], ρ * uc[1], ρ * uc[2], ρ * e_tot], dim=1).to(grid.FT)
+
+
+def ocean_gyre_state(problem, grid):
+    """``ocean_init_state!(::HBModel, ::OceanGyre)`` (ocean_gyre.jl:38-66): state at rest,
+    theta = (5 + 4 cos(pi y / Ly)) (1 + z / H).  Returns (Q (nreal,4,Np), aux MPIStateArray)."""
+    nr = grid.nrealelem
+    y, z = grid.vgeo[:nr, _X2], grid.vgeo[:nr, _X3]
+    Q = torch.zeros((nr, 4, grid.Np), dtype=grid.FT, device=grid.device)
+    Q[:, 3] = (5 + 4 * torch.cos(y * math.pi / problem.Lʸ)) * (1 + z / problem.H)
+    aux = MPIStateArray(grid, 8)
+    aux.data[:nr, 0] = y
+    return Q, aux

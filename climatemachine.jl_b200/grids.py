@@ -42,6 +42,28 @@ def spectralderivative(r):
     return D
 
 
+def indefinite_integral_interpolation_matrix(r, w):
+    """Grids.jl:1184-1206: row n integrates the interpolant from r[0] to r[n]."""
+    Nq = len(r)
+    diff = r[:, None] - r[None, :]
+    np.fill_diagonal(diff, 1.0)
+    wb = 1.0 / np.prod(diff, axis=1)
+    out = np.zeros((Nq, Nq))
+    for n in range(1, Nq):
+        rdst = (1 - r) / 2 * r[0] + (1 + r) / 2 * r[n]
+        I = np.zeros((Nq, Nq))
+        for k in range(Nq):
+            d = rdst[k] - r
+            hit = np.nonzero(d == 0)[0]
+            if hit.size:
+                I[k, hit[0]] = 1.0
+            else:
+                t = wb / d
+                I[k] = t / t.sum()
+        out[n] = (r[n] - r[0]) / 2 * (w @ I)
+    return out
+
+
 def _face_tables(Nq):
     Np = Nq ** 3
     p = np.arange(Np).reshape((Nq, Nq, Nq), order="F")
@@ -199,6 +221,8 @@ def build_grid(topology, N, FT=torch.float64, meshwarp=None, device="cuda"):
     g.elemtobndy = tt(t.elemtobndy.T)
     g.D = torch.as_tensor(np.ascontiguousarray(D.T), dtype=FT).to(dev)   # Julia memory order
     g.D_host, g.xi, g.w = D, xi, w
+    g.Imat = torch.as_tensor(np.ascontiguousarray(indefinite_integral_interpolation_matrix(xi, w).T),
+                             dtype=FT).to(dev)   # Julia memory order
     g.interiorelems, g.exteriorelems = tt(t.interiorelems), tt(t.exteriorelems)
     g.vmapsend, g.vmaprecv = tt(vmapsend), tt(vmaprecv)
     g.nabrtorank = [int(r) for r in t.nabrtorank]

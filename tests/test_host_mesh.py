@@ -148,3 +148,15 @@ def test_vortex_initial_condition():
     vg = pg.vgeo.numpy()
     oQ = setup(vg[:, 12], vg[:, 13], vg[:, 14], 0.0)
     assert np.allclose(Q, np.moveaxis(oQ, 0, 1), rtol=1e-13)
+
+
+def test_imat_and_filters_match_oracle():
+    from oracle import elements as oel, ocean as oocean
+    br = (np.linspace(0, 1, 3), np.linspace(0, 1, 3), np.linspace(-1, 0, 3))
+    pt = ptp.stacked_brick_topology(br, (False, False, False), ((1, 1), (1, 1), (2, 3)))
+    pg = pgrids.build_grid(pt, 4, device="cpu")
+    r, w = oel.lglpoints(np.float64, 4)
+    assert np.allclose(pg.Imat.numpy().T, oel.indefinite_integral_interpolation_matrix(r, w), atol=1e-15)
+    assert np.allclose(P.CutoffFilter(pg, 3).filter_matrix, oocean.cutoff_filter_matrix(r, 3), atol=1e-14)
+    assert np.allclose(P.ExponentialFilter(pg, 1, 8).filter_matrix,
+                       oocean.exponential_filter_matrix(r, 1, 8), atol=1e-14)
