@@ -217,8 +217,16 @@ def run_b200(args):
     barrier()
     norm0 = P.norm(Q)
     # keep the GPU busy until the sampler has produced its first lines (nvidia-smi start-up)
+    # (the decision is taken collectively: every rank must run the same number of steps, or the
+    # halo exchanges would no longer pair up)
     t_w = time.perf_counter()
-    while len(clocks.samples) < 2 and time.perf_counter() - t_w < 3.0:
+    while True:
+        more = torch.tensor([1.0 if (len(clocks.samples) < 2 and time.perf_counter() - t_w < 3.0) else 0.0],
+                            device=dev)
+        if world > 1:
+            dist.all_reduce(more, op=dist.ReduceOp.MIN)
+        if float(more) == 0.0:
+            break
         sol.dostep(Q, 0.0, nsteps=5)
         torch.cuda.synchronize()
     dg.set_timing(True)
