@@ -53,7 +53,7 @@ def _desc(P, **kw):
 
 
 @pytest.mark.parametrize("kw,code,msg", [
-    (dict(model=2), -2, b"unsupported balance law"),
+    (dict(model=3), -2, b"unsupported balance law"),
     (dict(N=7), -2, b"polynomial order"),
     (dict(nf_first=5), -2, b"numerical flux"),
     (dict(nstate=9), -2, b"tracers"),
