@@ -12,7 +12,7 @@ NF_RUSANOV, NF_CENTRAL, NF_ROE = 0, 1, 2
 ORIENT_NONE, ORIENT_FLAT, ORIENT_SPHERICAL = 0, 1, 2
 REF_NONE, REF_HYDROSTATIC = 0, 1
 TURB_CONSTANT_KINEMATIC, TURB_CONSTANT_DYNAMIC, TURB_SMAGORINSKY = 0, 1, 2
-SRC_GRAVITY, SRC_CORIOLIS = 1, 2
+SRC_GRAVITY, SRC_CORIOLIS, SRC_HELD_SUAREZ, SRC_RAYLEIGH_SPONGE = 1, 2, 4, 8
 BC_FREESLIP, BC_NOSLIP = 1, 2
 DIR_EVERY, DIR_HORIZONTAL = 0, 1
 
@@ -35,7 +35,10 @@ class cmdg_desc(C.Structure):
         ("ngradflux", C.c_int32),
         ("R_d", C.c_double), ("cp_d", C.c_double), ("cv_d", C.c_double), ("T_0", C.c_double),
         ("MSLP", C.c_double), ("grav", C.c_double), ("Omega", C.c_double),
-        ("inv_Pr_turb", C.c_double),
+        ("inv_Pr_turb", C.c_double), ("day", C.c_double),
+        ("sponge_z_max", C.c_double), ("sponge_z_sponge", C.c_double),
+        ("sponge_alpha_max", C.c_double), ("sponge_gamma", C.c_double),
+        ("sponge_u_relax", C.c_double * 3),
     ]
 
 

@@ -40,6 +40,7 @@ class EarthParameterSet:
     C_smag: float = 0.21
     T_surf_ref: float = 290.0
     T_min_ref: float = 220.0
+    day: float = 86400.0
 
     @property
     def R_d(self):
@@ -111,6 +112,23 @@ class Gravity:
 
 class Coriolis:
     pass
+
+
+class HeldSuarezForcing:
+    """experiments/AtmosGCM/heldsuarez.jl:112-172 (tutorials/Atmos/heldsuarez.jl:45-118)."""
+
+
+HeldSuarezForcingTutorial = HeldSuarezForcing
+
+
+@dataclass(frozen=True)
+class RayleighSponge:
+    """src/Atmos/Model/tendencies_momentum.jl:104-137."""
+    z_max: float
+    z_sponge: float
+    α_max: float
+    u_relaxation: Tuple = (0.0, 0.0, 0.0)
+    γ: float = 2.0
 
 
 # --- boundary conditions ---------------------------------------------------
@@ -217,8 +235,13 @@ class AtmosModel:
         if not isinstance(self.moisture, DryModel):
             raise UnsupportedModelError("only DryModel moisture is supported")
         for s in self.source:
-            if not isinstance(s, (Gravity, Coriolis)):
+            if not isinstance(s, (Gravity, Coriolis, HeldSuarezForcing, RayleighSponge)):
                 raise UnsupportedModelError(f"unsupported source {type(s).__name__}")
+        if sum(isinstance(s, RayleighSponge) for s in self.source) > 1:
+            raise UnsupportedModelError("at most one RayleighSponge source is supported")
+        if any(isinstance(s, (HeldSuarezForcing, RayleighSponge)) for s in self.source) and \
+                isinstance(self.orientation, NoOrientation):
+            raise UnsupportedModelError("HeldSuarezForcing / RayleighSponge need an orientation")
         for bc in self.boundaryconditions:
             if not (isinstance(bc, AtmosBC) and isinstance(bc.momentum, Impenetrable)
                     and isinstance(bc.momentum.drag, (FreeSlip, NoSlip))

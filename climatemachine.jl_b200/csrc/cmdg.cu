@@ -75,11 +75,13 @@ struct cmdg_handle_s {
   int Nq = 0, Np = 0, Nfp = 0;
   size_t fb = 8;  // bytes per float
   bool aux_model = false, visc = false;
+  int pf_dist = 296;      // L2 prefetch distance of the one-shot tendency kernel: 2 blocks per SM ahead (CMDG_PF overrides)
   bool use_pipe = false;  // experimental persistent pipelined kernel (CMDG_KERNEL=pipe); slower in round 1
   // caller-owned device arrays
   void *aux = nullptr, *gradflux = nullptr;
   // private device buffers
   void *vgeoP = nullptr, *sgeoP = nullptr, *Ddev = nullptr;
+  std::vector<double> Dhost;  // row-major D, mirrored into the constant-memory copy before launches
   int2 *conn = nullptr;
   int *interior = nullptr, *exterior = nullptr;
   int64_t ninterior = 0, nexterior = 0;
@@ -172,6 +174,12 @@ AtmosParams<R> make_params(const cmdg_handle_s *h) {
   P.a_T = c + 1;
   P.naux = c + 2;
   P.ngradflux = d.ngradflux;
+  P.inv_day = d.day > 0 ? (R)(R(1) / (R)d.day) : R(0);
+  P.sponge_z_max = (R)d.sponge_z_max;
+  P.sponge_z_sponge = (R)d.sponge_z_sponge;
+  P.sponge_alpha_max = (R)d.sponge_alpha_max;
+  P.sponge_gamma = (R)d.sponge_gamma;
+  for (int i = 0; i < 3; ++i) P.sponge_u[i] = (R)d.sponge_u_relax[i];
   return P;
 }
 
@@ -192,11 +200,29 @@ cudaEvent_t timing_event(cmdg_handle h) {
   return h->tev[h->tev_used++];
 }
 
-template <class R, int NQ, int NF1, bool AUX, bool VISC>
+// The constant-memory copy of D is per process: re-upload when another handle used it last.
+const cmdg_handle_s *g_constD_owner = nullptr;
+template <class R>
+int ensure_const_D(cmdg_handle h, cudaStream_t st) {
+  if (g_constD_owner == h) return 0;
+  if (sizeof(R) == 8) {
+    CU(cudaMemcpyToSymbolAsync(c_D64, h->Dhost.data(), 64 * sizeof(double), 0, cudaMemcpyHostToDevice, st));
+  } else {
+    static float tmp[64];
+    for (int i = 0; i < 64; ++i) tmp[i] = (float)h->Dhost[i];
+    CU(cudaMemcpyToSymbolAsync(c_D32, tmp, 64 * sizeof(float), 0, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  g_constD_owner = h;
+  return 0;
+}
+
+template <class R, int NQ, int NF1, bool AUX, bool VISC, bool SRCX = false>
 int launch_tend_inst(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P, int64_t n,
                      cudaStream_t st) {
   using SM = TendSmem<R, NQ, AUX, VISC>;
-  auto kern = dg_tendency_kernel<R, NQ, NF1, AUX, VISC>;
+  if (int rc = ensure_const_D<R>(h, st)) return rc;
+  auto kern = dg_tendency_kernel<R, NQ, NF1, AUX, VISC, SRCX>;
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
@@ -242,6 +268,10 @@ int launch_tend_nf(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P,
     return launch_tend_pipe<R, NQ, NF1, false>(h, a, P, n, st);
   }
   if (h->aux_model) {
+    if (P.sources & (SRC_HELD_SUAREZ | SRC_RAYLEIGH_SPONGE)) {
+      if (h->visc) return launch_tend_inst<R, NQ, NF1, true, true, true>(h, a, P, n, st);
+      return launch_tend_inst<R, NQ, NF1, true, false, true>(h, a, P, n, st);
+    }
     if (h->visc) return launch_tend_inst<R, NQ, NF1, true, true>(h, a, P, n, st);
     return launch_tend_inst<R, NQ, NF1, true, false>(h, a, P, n, st);
   }
@@ -439,6 +469,7 @@ TendArgs<R> base_args(cmdg_handle h) {
   a.conn = h->conn;
   a.D = (const R *)h->Ddev;
   a.aux_out = h->d.write_aux_diagnostics ? (R *)h->aux : nullptr;
+  a.pf_dist = h->pf_dist;
   return a;
 }
 
@@ -693,6 +724,8 @@ int bind_grid_t(cmdg_handle h, const void *vgeo, const void *sgeo, const void *D
     for (int b = 0; b < NQ; ++b) Dr[a * NQ + b] = Dj[a + NQ * b];
   CU(cudaMalloc(&h->Ddev, Dr.size() * sizeof(R)));
   CU(cudaMemcpy(h->Ddev, Dr.data(), Dr.size() * sizeof(R), cudaMemcpyHostToDevice));
+  h->Dhost.assign(64, 0.0);
+  for (size_t i = 0; i < Dr.size(); ++i) h->Dhost[i] = (double)Dr[i];
   CU(cudaDeviceSynchronize());
   return 0;
 }
@@ -775,8 +808,14 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
       d->ref_state < 0 || d->ref_state > CMDG_REF_HYDROSTATIC ||
       d->turbulence < 0 || d->turbulence > CMDG_TURB_SMAGORINSKY)
     return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported orientation / reference state / turbulence model");
-  if (d->sources & ~(CMDG_SRC_GRAVITY | CMDG_SRC_CORIOLIS))
+  if (d->sources & ~(CMDG_SRC_GRAVITY | CMDG_SRC_CORIOLIS | CMDG_SRC_HELD_SUAREZ | CMDG_SRC_RAYLEIGH_SPONGE))
     return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported source term");
+  if ((d->sources & (CMDG_SRC_HELD_SUAREZ | CMDG_SRC_RAYLEIGH_SPONGE)) && d->orientation == CMDG_ORIENT_NONE)
+    return fail(nullptr, CMDG_ERR_INVALID, "HeldSuarezForcing / RayleighSponge need an orientation");
+  if ((d->sources & CMDG_SRC_HELD_SUAREZ) && !(d->day > 0))
+    return fail(nullptr, CMDG_ERR_INVALID, "HeldSuarezForcing needs cmdg_desc.day > 0");
+  if ((d->sources & CMDG_SRC_RAYLEIGH_SPONGE) && !(d->sponge_z_max > d->sponge_z_sponge))
+    return fail(nullptr, CMDG_ERR_INVALID, "RayleighSponge needs z_max > z_sponge");
   if ((d->sources & CMDG_SRC_GRAVITY) && d->orientation == CMDG_ORIENT_NONE)
     return fail(nullptr, CMDG_ERR_INVALID, "Gravity needs an orientation");
   if (d->ref_state == CMDG_REF_HYDROSTATIC && d->orientation == CMDG_ORIENT_NONE)
@@ -808,6 +847,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   const bool zero_visc = d->turbulence != CMDG_TURB_SMAGORINSKY && d->turb_param == 0.0;
   h->visc = !(d->skip_zero_viscosity && zero_visc);
   if (const char *kv = getenv("CMDG_KERNEL")) h->use_pipe = std::string(kv) == "pipe";
+  if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
   cudaError_t e1 = cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
   cudaError_t e2 = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
   cudaError_t e3 = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
@@ -820,6 +860,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
 }
 
 int cmdg_destroy(cmdg_handle h) {
+  if (g_constD_owner == h) g_constD_owner = nullptr;
   if (!h) return CMDG_OK;
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,

@@ -33,7 +33,7 @@ namespace cmdg {
 
 enum { NF_RUSANOV = 0, NF_CENTRAL = 1, NF_ROE = 2 };
 enum { TURB_CONST_KINEMATIC = 0, TURB_CONST_DYNAMIC = 1, TURB_SMAGORINSKY = 2 };
-enum { SRC_GRAVITY = 1, SRC_CORIOLIS = 2 };
+enum { SRC_GRAVITY = 1, SRC_CORIOLIS = 2, SRC_HELD_SUAREZ = 4, SRC_RAYLEIGH_SPONGE = 8 };
 enum { BC_FREESLIP = 1, BC_NOSLIP = 2 };
 
 // Uniform (per launch) physics parameters of the dry AtmosModel.
@@ -52,6 +52,8 @@ struct AtmosParams {
   // auxiliary-state column ids (0-based), -1 when absent
   int a_Phi, a_gradPhi, a_ref_rho, a_ref_p, a_Delta, a_theta_v, a_T;
   int naux, ngradflux;
+  // HeldSuarezForcing / RayleighSponge (SRCX kernels only)
+  R inv_day, sponge_z_max, sponge_z_sponge, sponge_alpha_max, sponge_gamma, sponge_u[3];
 };
 
 template <class R>
@@ -70,6 +72,7 @@ struct TendArgs {
   R alpha, beta;       // dQ = alpha*RHS + beta*dQ
   R rkb_dt;            // Qout = Q + rkb_dt * dQ
   R t;
+  int pf_dist;         // L2 prefetch distance in launch-list entries (0 = off)
 };
 
 // conn.y layout: bits 0-2 neighbour face (0..5), bit 3 flip of first face index,
@@ -256,6 +259,15 @@ __device__ __forceinline__ void roe_dissipation(const AtmosParams<R> &P, const R
              w3 * (utut * R(0.5) + Phi - P.T_0 * P.cv_d) + w4 * (utdu - utn * dun)) * R(0.5);
 }
 
+// Derivative matrix in constant memory (row-major copy of Julia's D, at most 8 x 8): the
+// contraction reads it through the constant cache (LDC), which keeps ~110 shared-memory
+// wavefronts per element off the LSU data pipe -- the unit that bounds the tendency kernel.
+__constant__ double c_D64[64];
+__constant__ float c_D32[64];
+template <class R> __device__ __forceinline__ R const_D(int idx);
+template <> __device__ __forceinline__ double const_D<double>(int idx) { return c_D64[idx]; }
+template <> __device__ __forceinline__ float const_D<float>(int idx) { return c_D32[idx]; }
+
 template <int NQ>
 struct Dims {
   static constexpr int NP = NQ * NQ * NQ;
@@ -275,6 +287,16 @@ struct Dims {
 // is compiled in: NF1 numerical flux, AUX = model has orientation/reference-state columns,
 // VISC = second-order fluxes from the gradient-flux array are included.
 // ---------------------------------------------------------------------------------------
+// Pull [p, p+bytes) into L2, one 128-byte line per thread (no registers or shared memory are
+// tied up, nothing waits on it).
+template <int BLOCK>
+__device__ __forceinline__ void prefetch_l2_range(const void *p, size_t bytes, int tid) {
+  const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)127;
+  const int lines = (int)(((uintptr_t)p + bytes - a0 + 127) >> 7);
+  for (int l = tid; l < lines; l += BLOCK)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + ((uintptr_t)l << 7)));
+}
+
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -301,7 +323,52 @@ struct TendSmem {
 #ifndef CMDG_TEND_MINBLOCKS
 #define CMDG_TEND_MINBLOCKS 5
 #endif
-template <class R, int NQ, int NF1, bool AUX, bool VISC>
+template <class R> __device__ __forceinline__ R log_(R x);
+template <> __device__ __forceinline__ double log_(double x) { return log(x); }
+template <> __device__ __forceinline__ float log_(float x) { return logf(x); }
+template <class R> __device__ __forceinline__ R sinpi_(R x);
+template <> __device__ __forceinline__ double sinpi_(double x) { return sinpi(x); }
+template <> __device__ __forceinline__ float sinpi_(float x) { return sinpif(x); }
+
+// HeldSuarezForcing (experiments/AtmosGCM/heldsuarez.jl:112-172) and RayleighSponge
+// (src/Atmos/Model/tendencies_momentum.jl:104-137) added to src[1..4].  sin(lat) = x3/|x|
+// (Orientations.jl:178-179) is used directly instead of sin(asin(.)).
+template <class R>
+__device__ __forceinline__ void extended_sources(const AtmosParams<R> &P, const R q[5],
+                                                 const Thermo<R> &th, R Phi, const R gPhi[3],
+                                                 const R x[3], R src[5]) {
+  if (P.sources & SRC_HELD_SUAREZ) {
+    const R k_a = P.inv_day / R(40), k_f = P.inv_day, k_s = P.inv_day / R(4);
+    const R s2 = x[2] * x[2] / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // sin^2(lat)
+    const R c2 = R(1) - s2;
+    const R sigma = th.p / P.MSLP;
+    const R exner = pow_<R>(sigma, P.kappa);
+    const R sigma_b = R(7) / R(10);
+    const R dsig = (sigma - sigma_b) / (R(1) - sigma_b);
+    const R hf = dsig > R(0) ? dsig : R(0);
+    R T_eq = (R(315) - R(60) * s2 - R(10) * log_<R>(sigma) * c2) * exner;
+    T_eq = T_eq > R(200) ? T_eq : R(200);
+    const R k_T = k_a + (k_s - k_a) * hf * (c2 * c2);
+    const R k_v = k_f * hf;
+    const R ig = R(1) / P.grav;
+    const R nh[3] = {gPhi[0] * ig, gPhi[1] * ig, gPhi[2] * ig};
+    const R nd = nh[0] * q[1] + nh[1] * q[2] + nh[2] * q[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) src[1 + d] += -k_v * (q[1 + d] - nh[d] * nd);
+    src[4] += -k_T * q[0] * P.cv_d * (th.T - T_eq);
+  }
+  if (P.sources & SRC_RAYLEIGH_SPONGE) {
+    const R z = Phi / P.grav;
+    if (z >= P.sponge_z_sponge) {
+      const R r = (z - P.sponge_z_sponge) / (P.sponge_z_max - P.sponge_z_sponge);
+      const R beta = P.sponge_alpha_max * pow_<R>(sinpi_<R>(r / 2), P.sponge_gamma);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) src[1 + d] += -beta * (q[1 + d] - q[0] * P.sponge_u[d]);
+    }
+  }
+}
+
+template <class R, int NQ, int NF1, bool AUX, bool VISC, bool SRCX>
 __global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (VISC ? 4 : CMDG_TEND_MINBLOCKS) : 1))
 dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
@@ -326,6 +393,27 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     cn[r] = (it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
   }
   if (tid < NQ * NQ) S.D[tid] = A.D[tid];
+
+  // ---- L2 prefetch for the block that will replace this one on the SM: the one-shot kernel
+  // is latency-bound (two dependent DRAM round trips per block); with the own-element data
+  // already in L2 those become L2 hits and DRAM stays busy during the compute phases ----
+  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x) {
+    const int bn = blockIdx.x + A.pf_dist;
+    const int en = A.elems ? A.elems[bn] : bn;
+    prefetch_l2_range<BLOCK>(Qg + (size_t)en * 5 * NP, 5 * NP * sizeof(R), tid);
+    prefetch_l2_range<BLOCK>(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R), tid);
+    prefetch_l2_range<BLOCK>(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R), tid);
+    if (A.beta != R(0)) prefetch_l2_range<BLOCK>(A.dQ + (size_t)en * 5 * NP, 5 * NP * sizeof(R), tid);
+    if (AUX) {
+      const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
+      const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
+      if (lo >= 0 && hi > lo)
+        prefetch_l2_range<BLOCK>(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R), tid);
+    }
+    if (VISC)
+      prefetch_l2_range<BLOCK>(A.gradflux + (size_t)en * P.ngradflux * NP, (size_t)P.ngradflux * NP * sizeof(R), tid);
+    if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
+  }
 
   // ---- (b) issue my node's loads ----
   R MI = 0;
@@ -441,6 +529,16 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       src[1] += P.two_Omega * q[2];
       src[2] -= P.two_Omega * q[1];
     }
+    if (AUX && SRCX) {
+      R x[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[d] = auxg[eoffA + (size_t)d * NP + tid];
+      if (!(VISC || (P.sources & SRC_GRAVITY))) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gPhi[d] = auxg[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
+      }
+      extended_sources<R>(P, q, th, Phi, gPhi, x, src);
+    }
   }
   __syncthreads();
 
@@ -456,7 +554,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   if (tid < NP) {
 #pragma unroll
     for (int n = 0; n < NQ; ++n) {
+#ifdef CMDG_D_SHARED
       const R d1 = S.D[n * NQ + i], d2 = S.D[n * NQ + j], d3 = S.D[n * NQ + k];
+#else
+      const R d1 = const_D<R>(n * NQ + i), d2 = const_D<R>(n * NQ + j), d3 = const_D<R>(n * NQ + k);
+#endif
       const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
 #pragma unroll
       for (int s = 0; s < 5; ++s)
@@ -568,35 +670,21 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 
   // ---- combine: tendency[vid-] -= vMI sM F*  in face order 1..6, then alpha/beta, RK ----
   if (tid < NP) {
-    if (i == 0) {
-      const int it = 0 * NFP + j + NQ * k;
+    // a node lies on at most one face per direction: three predicated reads instead of six
+    const int it1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
+    const int it2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
+    const int it3 = (k == 0) ? 4 * NFP + i + NQ * j : ((k == NQ - 1) ? 5 * NFP + i + NQ * j : -1);
+    if (it1 >= 0) {
 #pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it1];
     }
-    if (i == NQ - 1) {
-      const int it = 1 * NFP + j + NQ * k;
+    if (it2 >= 0) {
 #pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it2];
     }
-    if (j == 0) {
-      const int it = 2 * NFP + i + NQ * k;
+    if (it3 >= 0) {
 #pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
-    }
-    if (j == NQ - 1) {
-      const int it = 3 * NFP + i + NQ * k;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
-    }
-    if (k == 0) {
-      const int it = 4 * NFP + i + NQ * j;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
-    }
-    if (k == NQ - 1) {
-      const int it = 5 * NFP + i + NQ * j;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it];
+      for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it3];
     }
 #pragma unroll
     for (int s = 0; s < 5; ++s) {

@@ -166,8 +166,16 @@ class DGModel:
             d.turbulence, d.turb_param = _lib.TURB_SMAGORINSKY, t.C_smag
         else:
             raise bl.UnsupportedModelError(f"turbulence closure {type(t).__name__} is not supported")
-        d.sources = sum({bl.Gravity: _lib.SRC_GRAVITY, bl.Coriolis: _lib.SRC_CORIOLIS}[type(s)]
-                        for s in m.source)
+        d.sources = 0
+        for s in m.source:
+            d.sources |= {bl.Gravity: _lib.SRC_GRAVITY, bl.Coriolis: _lib.SRC_CORIOLIS,
+                          bl.HeldSuarezForcing: _lib.SRC_HELD_SUAREZ,
+                          bl.RayleighSponge: _lib.SRC_RAYLEIGH_SPONGE}[type(s)]
+            if isinstance(s, bl.RayleighSponge):
+                d.sponge_z_max, d.sponge_z_sponge = s.z_max, s.z_sponge
+                d.sponge_alpha_max, d.sponge_gamma = s.α_max, s.γ
+                for i in range(3):
+                    d.sponge_u_relax[i] = s.u_relaxation[i]
         d.diffusion_direction = (_lib.DIR_HORIZONTAL if isinstance(self.diffusion_direction, bl.HorizontalDirection)
                                  else _lib.DIR_EVERY)
         d.skip_zero_viscosity = int(skip_zero_viscosity)
@@ -180,6 +188,7 @@ class DGModel:
         p = m.param_set
         d.R_d, d.cp_d, d.cv_d, d.T_0 = p.R_d, p.cp_d, p.cv_d, p.T_0
         d.MSLP, d.grav, d.Omega, d.inv_Pr_turb = p.MSLP, p.grav, p.Omega, p.inv_Pr_turb
+        d.day = p.day
         self._desc = d
         self._h = C.c_void_p()
         _lib.check(L.cmdg_create(C.byref(d), C.byref(self._h)))

@@ -56,8 +56,9 @@ enum { CMDG_ORIENT_NONE = 0, CMDG_ORIENT_FLAT = 1, CMDG_ORIENT_SPHERICAL = 2 };
 enum { CMDG_REF_NONE = 0, CMDG_REF_HYDROSTATIC = 1 };
 /* src/Common/TurbulenceClosures/TurbulenceClosures.jl:287-499 */
 enum { CMDG_TURB_CONSTANT_KINEMATIC = 0, CMDG_TURB_CONSTANT_DYNAMIC = 1, CMDG_TURB_SMAGORINSKY = 2 };
-/* src/Atmos/Model/tendencies_momentum.jl:62-92 */
-enum { CMDG_SRC_GRAVITY = 1, CMDG_SRC_CORIOLIS = 2 };
+/* src/Atmos/Model/tendencies_momentum.jl:62-92 (Gravity, Coriolis), :104-137 (RayleighSponge);
+ * HeldSuarezForcing: experiments/AtmosGCM/heldsuarez.jl:112-172 (= tutorials/Atmos/heldsuarez.jl:45-118) */
+enum { CMDG_SRC_GRAVITY = 1, CMDG_SRC_CORIOLIS = 2, CMDG_SRC_HELD_SUAREZ = 4, CMDG_SRC_RAYLEIGH_SPONGE = 8 };
 /* src/Atmos/Model/bc_momentum.jl:1-80 with Insulating energy (bc_energy.jl:10-17) */
 enum { CMDG_BC_FREESLIP = 1, CMDG_BC_NOSLIP = 2 };
 /* DGModel.direction / diffusion_direction (src/Numerics/DGMethods/DGModel.jl:3-19) */
@@ -100,6 +101,9 @@ typedef struct {
   int32_t nstate, naux, ngrad, ngradflux;
   /* CLIMAParameters.Planet values */
   double R_d, cp_d, cv_d, T_0, MSLP, grav, Omega, inv_Pr_turb;
+  double day;             /* CLIMAParameters.Planet.day (HeldSuarezForcing rates) */
+  /* RayleighSponge{FT}(z_max, z_sponge, alpha_max, u_relaxation, gamma) */
+  double sponge_z_max, sponge_z_sponge, sponge_alpha_max, sponge_gamma, sponge_u_relax[3];
 } cmdg_desc;
 
 /*

@@ -9,7 +9,10 @@ Vectorised NumPy restatement of the dry/compressible subset of
   ``grad h_tot[3], S[6] (11,21,31,22,32,33), [N2]``
 * first-order fluxes ``tendencies_mass.jl:7-9``, ``tendencies_momentum.jl:13-30``,
   ``tendencies_energy.jl:7-21`` summed by ``BalanceLaws/kernels.jl:31-53``
-* sources Gravity / Coriolis ``tendencies_momentum.jl:66-92``
+* sources Gravity / Coriolis ``tendencies_momentum.jl:66-92``, RayleighSponge ``:104-137``,
+  HeldSuarezForcing ``experiments/AtmosGCM/heldsuarez.jl:112-172`` (= the tutorial's
+  ``HeldSuarezForcingTutorial``, ``tutorials/Atmos/heldsuarez.jl:45-118``) with
+  ``latitude``/``projection_tangential`` of ``src/Common/Orientations/Orientations.jl:73-99,178-179``
 * ``wavespeed`` ``AtmosModel.jl:776-796``
 * thermodynamic state ``thermo_states.jl:67-77``, ``moisture.jl:32-69``
 * gradient argument / flux ``AtmosModel.jl:622-744``, ``energy.jl:20-59``,
@@ -100,7 +103,9 @@ class DryAtmosModel:
         self.orientation = orientation            # none | flat | spherical
         self.ref_state = ref_state                # None or dict(T_surf,T_min,H_t,subtract_off)
         self.turbulence = turbulence
-        self.sources = tuple(sources)             # subset of ("gravity", "coriolis")
+        # entries: "gravity" | "coriolis" | "held_suarez" |
+        # ("rayleigh_sponge", z_max, z_sponge, alpha_max, (u1,u2,u3), gamma), summed in tuple order
+        self.sources = tuple(sources)
         self.bcs = tuple(bcs)                     # per boundary tag: "freeslip" | "noslip"
         # auxiliary layout
         c = 3
@@ -173,12 +178,52 @@ class DryAtmosModel:
             # -(0,0,2Ω) x ρu
             cx = np.stack([0 * ρu[2] - w * ρu[1], w * ρu[0] - 0 * ρu[2], 0 * ρu[1] - 0 * ρu[0]])
             srcs.append(-cx)
+        FT = self.FT
+        for s in self.sources:
+            if s == "held_suarez":
+                k_v, k_T, T_equil = self.held_suarez_coefficients(Q, aux)
+                ρu = Q[1:4]
+                n̂ = aux[self.a_gradΦ] / self.ps.grav
+                proj_n = n̂ * (n̂[0] * ρu[0] + n̂[1] * ρu[1] + n̂[2] * ρu[2])
+                srcs.append(-k_v * (ρu - proj_n))
+                T, _ = self.thermo(Q, aux)
+                S[4] = -k_T * Q[0] * self.ps.cv_d * (T - T_equil)
+            elif isinstance(s, tuple) and s[0] == "rayleigh_sponge":
+                _, z_max, z_sponge, α_max, u_relax, γ = s
+                z = self.Φ(aux) / self.ps.grav
+                r = (z - FT(z_sponge)) / (FT(z_max) - FT(z_sponge))
+                with np.errstate(invalid="ignore"):
+                    β = FT(α_max) * np.sin(np.pi * (r / 2)) ** FT(γ)
+                β = np.where(z >= FT(z_sponge), β, 0 * β)
+                ur = np.asarray(u_relax, dtype=Q.dtype).reshape((3,) + (1,) * (Q.ndim - 1))
+                srcs.append(-β * (Q[1:4] - Q[0] * ur))
         if srcs:
             tot = srcs[0]
             for s in srcs[1:]:
                 tot = tot + s
             S[1:4] = tot
         return S
+
+    def held_suarez_coefficients(self, Q, aux):
+        """(k_v, k_T, T_equil) of ``held_suarez_forcing_coefficients``
+        (experiments/AtmosGCM/heldsuarez.jl:116-153)."""
+        ps, FT = self.ps, self.FT
+        k_a = FT(1 / (40 * ps.day))
+        k_f = FT(1 / ps.day)
+        k_s = FT(1 / (4 * ps.day))
+        ΔT_y, Δθ_z, T_equator, T_min, σ_b = FT(60), FT(10), FT(315), FT(200), FT(7 / 10)
+        x = aux[self.a_coord]
+        φ = np.arcsin(x[2] / np.sqrt(x[0] ** 2 + x[1] ** 2 + x[2] ** 2))
+        _, p = self.thermo(Q, aux)
+        σ = p / ps.MSLP
+        exner_p = σ ** (ps.R_d / ps.cp_d)
+        Δσ = (σ - σ_b) / (1 - σ_b)
+        height_factor = np.maximum(0, Δσ)
+        T_equil = (T_equator - ΔT_y * np.sin(φ) ** 2 - Δθ_z * np.log(σ) * np.cos(φ) ** 2) * exner_p
+        T_equil = np.maximum(T_min, T_equil)
+        k_T = k_a + (k_s - k_a) * height_factor * np.cos(φ) ** 4
+        k_v = k_f * height_factor
+        return k_v, k_T, T_equil
 
     def wavespeed(self, n, Q, aux):
         u = (1 / Q[0]) * Q[1:4]

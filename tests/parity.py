@@ -54,7 +54,10 @@ def device_model(om):
     turb = {"constant_dynamic": lambda: P.ConstantDynamicViscosity(float(k[1]), bool(k[2])),
             "constant_kinematic": lambda: P.ConstantKinematicViscosity(float(k[1]), bool(k[2])),
             "smagorinsky": lambda: P.SmagorinskyLilly(float(k[1]))}[k[0]]()
-    src = tuple({"gravity": P.Gravity, "coriolis": P.Coriolis}[s]() for s in om.sources)
+    src = tuple(P.RayleighSponge(float(s[1]), float(s[2]), float(s[3]), tuple(float(x) for x in s[4]), float(s[5]))
+                if isinstance(s, tuple) else
+                {"gravity": P.Gravity, "coriolis": P.Coriolis, "held_suarez": P.HeldSuarezForcing}[s]()
+                for s in om.sources)
     bcs = tuple(P.AtmosBC(P.Impenetrable(P.FreeSlip() if b == "freeslip" else P.NoSlip())) for b in om.bcs)
     return P.AtmosModel(orientation=orient, ref_state=ref, turbulence=turb, source=src,
                         boundaryconditions=bcs)
@@ -209,6 +212,23 @@ def gcm_case(nf="rusanov", nsteps=1, dt=0.5, turbulence=("constant_kinematic", 0
     return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
                         diffusion_direction=diffusion_direction,
                         skip_zero_viscosity=skip_zero_viscosity)
+
+
+def heldsuarez_case(nf="rusanov", nsteps=1, dt=0.5, turbulence=("smagorinsky", 0.21),
+                    diffusion_direction="horizontal", ne=3, nvert=3):
+    """Held-Suarez dry GCM (tutorials/Atmos/heldsuarez.jl:160-201 without hyperdiffusion, explicit
+    stepping): Smagorinsky + Gravity, Coriolis, HeldSuarezForcing, RayleighSponge(30 km, 12 km,
+    1/900 s, 0, 2); state = reference state + smooth wind/temperature perturbation so that every
+    forcing term (relaxation, boundary-layer friction, sponge) is active."""
+    model, gs = gcm_setup(ne, nvert, turbulence=turbulence)
+    model.sources = ("gravity", "coriolis", "held_suarez",
+                     ("rayleigh_sponge", 30e3, 12e3, 1 / 60 / 15, (0.0, 0.0, 0.0), 2.0))
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], nf, diffusion_direction=diffusion_direction)
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_baroclinic_wave(model, aux)
+    return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                        diffusion_direction=diffusion_direction, skip_zero_viscosity=False)
 
 
 def box_setup(nelem=(3, 2, 3), FT=np.float64, turbulence=("smagorinsky", 0.21), csize=1,

@@ -57,7 +57,7 @@ def _desc(P, **kw):
     (dict(N=7), -2, b"polynomial order"),
     (dict(nf_first=5), -2, b"numerical flux"),
     (dict(nstate=9), -2, b"tracers"),
-    (dict(sources=4), -2, b"source"),
+    (dict(sources=16), -2, b"source"),
     (dict(naux=16), -1, b"naux"),
     (dict(float_bytes=2), -2, b"Float64 or Float32"),
 ])

@@ -100,6 +100,16 @@ def test_held_suarez_like_smagorinsky_sphere():
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+@pytest.mark.parametrize("turbulence", [("smagorinsky", 0.21), ("constant_kinematic", 0.0, False)])
+def test_held_suarez_forcing_and_sponge(turbulence):
+    """Config (4) as tutorials/Atmos/heldsuarez.jl sets it (hyperdiffusion off): Gravity, Coriolis,
+    HeldSuarezForcing and RayleighSponge sources on top of the Smagorinsky second-order path."""
+    res = parity.heldsuarez_case(turbulence=turbulence, nsteps=2, dt=0.5)
+    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
+    assert res["tendency_inc_rel_l2"] <= TOL_TEND_F64, res
+    assert res["state_rel_l2"] <= 1e-12, res
+
+
 def test_multi_gpu_halo_and_parity():
     """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU box skips it, `gpurun --gpus 2` runs it)."""
     import os
