@@ -76,7 +76,6 @@ struct cmdg_handle_s {
   size_t fb = 8;  // bytes per float
   bool aux_model = false, visc = false;
   int pf_dist = 296;      // L2 prefetch distance of the one-shot tendency kernel: 2 blocks per SM ahead (CMDG_PF overrides)
-  bool use_pipe = false;  // experimental persistent pipelined kernel (CMDG_KERNEL=pipe); slower in round 1
   // caller-owned device arrays
   void *aux = nullptr, *gradflux = nullptr;
   // private device buffers
@@ -236,37 +235,9 @@ int launch_tend_inst(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &
   return 0;
 }
 
-template <class R, int NQ, int NF1, bool AUX>
-int launch_tend_pipe(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P, int64_t n,
-                     cudaStream_t st) {
-  using SM = PipeSmem<R, NQ, AUX>;
-  auto kern = dg_tendency_pipe_kernel<R, NQ, NF1, AUX>;
-  static int blocks_per_sm = 0, nsm = 0;
-  if (!blocks_per_sm) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 160, sizeof(SM)));
-    if (blocks_per_sm < 1) return fail(h, CMDG_ERR_CUDA, "pipelined tendency kernel does not fit on an SM");
-  }
-  const int64_t grid = std::min<int64_t>(n, (int64_t)nsm * blocks_per_sm);
-  if (h->timing) cudaEventRecord(timing_event(h), st);
-  kern<<<(unsigned)grid, 160, sizeof(SM), st>>>(a, P, (int)n);
-  if (h->timing) cudaEventRecord(timing_event(h), st);
-  CU(cudaGetLastError());
-  h->launches++;
-  return 0;
-}
-
 template <class R, int NQ, int NF1>
 int launch_tend_nf(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &P, int64_t n,
                    cudaStream_t st) {
-  if (!h->visc && h->use_pipe) {
-    if (h->aux_model) return launch_tend_pipe<R, NQ, NF1, true>(h, a, P, n, st);
-    return launch_tend_pipe<R, NQ, NF1, false>(h, a, P, n, st);
-  }
   if (h->aux_model) {
     if (P.sources & (SRC_HELD_SUAREZ | SRC_RAYLEIGH_SPONGE)) {
       if (h->visc) return launch_tend_inst<R, NQ, NF1, true, true, true>(h, a, P, n, st);
@@ -846,7 +817,6 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   h->aux_model = d->orientation != CMDG_ORIENT_NONE || d->ref_state != CMDG_REF_NONE;
   const bool zero_visc = d->turbulence != CMDG_TURB_SMAGORINSKY && d->turb_param == 0.0;
   h->visc = !(d->skip_zero_viscosity && zero_visc);
-  if (const char *kv = getenv("CMDG_KERNEL")) h->use_pipe = std::string(kv) == "pipe";
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
   cudaError_t e1 = cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
   cudaError_t e2 = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);

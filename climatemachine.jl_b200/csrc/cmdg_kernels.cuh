@@ -317,7 +317,6 @@ struct TendSmem {
   R Ap[2][AUX ? NFN : 1];                  // neighbour geopotential, reference pressure
   R GF[VISC ? 10 : 1][VISC ? NP : 1];      // own gradient flux
   R GFp[VISC ? 10 : 1][VISC ? NFN : 1];    // neighbour gradient flux
-  R D[NQ * NQ];
 };
 
 #ifndef CMDG_TEND_MINBLOCKS
@@ -374,7 +373,10 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
   constexpr int NGF = 10;  // max gradient-flux columns
-  constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
+  constexpr int NWARP = BLOCK / 32;
+  constexpr int FSTRIDE = (NWARP - 1) * 32;              // face threads per block
+  constexpr int NITEM = (NFN + FSTRIDE - 1) / FSTRIDE;   // face items per face thread
+  static_assert(NWARP >= 2 && NQ * 5 <= 32, "plane contraction: one warp holds Nq x 5 (plane, state) pairs");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TendSmem<R, NQ, AUX, VISC> &S = *reinterpret_cast<TendSmem<R, NQ, AUX, VISC> *>(smem_raw);
 
@@ -386,13 +388,19 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   const R *__restrict__ auxg = A.aux;
 
   // ---- (a) face descriptors of my face items ----
+  // Warp specialisation: after the node phase one warp (rotating with the block index, so
+  // that the four schedulers share that work) contracts the fluxes with D plane by plane while
+  // the other warps compute the numerical fluxes of the 6 * Nfp face items.  A face thread
+  // gathers (cp.async) the neighbour traces of exactly the items it will later compute.
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cw = blockIdx.x % NWARP;
+  const int ft = (warp == cw) ? -1 : ((warp < cw ? warp : warp - 1) * 32 + lane);
   int2 cn[NITEM];
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = tid + r * BLOCK;
-    cn[r] = (it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
+    const int it = ft + r * FSTRIDE;
+    cn[r] = (ft >= 0 && it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
   }
-  if (tid < NQ * NQ) S.D[tid] = A.D[tid];
 
   // ---- L2 prefetch for the block that will replace this one on the SM: the one-shot kernel
   // is latency-bound (two dependent DRAM round trips per block); with the own-element data
@@ -449,8 +457,8 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   // ---- (c) asynchronous gathers of the neighbour traces into shared memory ----
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = tid + r * BLOCK;
-    if (it < NFN && ((cn[r].y >> 4) & 15) == 0) {
+    const int it = ft + r * FSTRIDE;
+    if (ft >= 0 && it < NFN && ((cn[r].y >> 4) & 15) == 0) {
       const int fn = it % NFP;
       int a = fn % NQ;
       const int b = fn / NQ;
@@ -548,31 +556,64 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     for (int s = 0; s < 5; ++s) dQold[s] = A.dQ[eoffQ + (size_t)s * NP + tid];
   }
 
-  // ---- volume: weak derivative  MI * D^T (M xi . F) ----
-  R acc[5] = {0, 0, 0, 0, 0};
+  // ---- volume: weak derivative  D^T (M xi . F), by the contraction warp ----
+  // Lane (k, s) owns the k-plane of state s: the xi1- and xi2-contractions stay inside the plane
+  // (each flux value is loaded once and D comes from the constant bank as an immediate
+  // operand), only xi3 reads the other planes: 7 shared loads per output instead of 18.  The
+  // tendency kernel is bound by the LSU data pipe, so this -- not the flops -- is what counts.
+  // The result replaces the F[0] plane the lane has just consumed.
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
-  if (tid < NP) {
+  if (warp == cw) {
+    if (lane < NQ * 5) {
+      const int pk = lane % NQ, ps = lane / NQ;
+      R dk[NQ];
 #pragma unroll
-    for (int n = 0; n < NQ; ++n) {
-#ifdef CMDG_D_SHARED
-      const R d1 = S.D[n * NQ + i], d2 = S.D[n * NQ + j], d3 = S.D[n * NQ + k];
-#else
-      const R d1 = const_D<R>(n * NQ + i), d2 = const_D<R>(n * NQ + j), d3 = const_D<R>(n * NQ + k);
-#endif
-      const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
+      for (int n = 0; n < NQ; ++n) dk[n] = const_D<R>(n * NQ + pk);
+      R pa[NQ][NQ];
 #pragma unroll
-      for (int s = 0; s < 5; ++s)
-        acc[s] += d1 * S.F[0][s][o1] + d2 * S.F[1][s][o2] + d3 * S.F[2][s][o3];
+      for (int b = 0; b < NQ; ++b)
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) pa[b][a] = R(0);
+      R *F1 = &S.F[0][ps][NQ * NQ * pk];
+      const R *F2 = &S.F[1][ps][NQ * NQ * pk];
+      const R *F3 = &S.F[2][ps][0];
+#pragma unroll
+      for (int b = 0; b < NQ; ++b) {
+        R f[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) f[n] = F1[n + NQ * b];
+#pragma unroll
+        for (int a = 0; a < NQ; ++a)
+#pragma unroll
+          for (int n = 0; n < NQ; ++n) pa[b][a] += const_D<R>(n * NQ + a) * f[n];
+      }
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) {
+        R f[NQ];
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) f[a] = F2[a + NQ * n];
+#pragma unroll
+        for (int b = 0; b < NQ; ++b)
+#pragma unroll
+          for (int a = 0; a < NQ; ++a) pa[b][a] += const_D<R>(n * NQ + b) * f[a];
+      }
+#pragma unroll
+      for (int n = 0; n < NQ; ++n)
+#pragma unroll
+        for (int b = 0; b < NQ; ++b)
+#pragma unroll
+          for (int a = 0; a < NQ; ++a) pa[b][a] += dk[n] * F3[a + NQ * b + NQ * NQ * n];
+#pragma unroll
+      for (int b = 0; b < NQ; ++b)
+#pragma unroll
+        for (int a = 0; a < NQ; ++a) F1[a + NQ * b] = pa[b][a];
     }
-#pragma unroll
-    for (int s = 0; s < 5; ++s) acc[s] = MI * acc[s] + src[s];
-  }
-
+  } else {
   // ---- faces: numerical flux at every face node of this element ----
   cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = tid + r * BLOCK;
+    const int it = ft + r * FSTRIDE;
     if (it >= NFN) break;
     const int f = it / NFP, fn = it - f * NFP;
     const int2 c = cn[r];
@@ -666,10 +707,14 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) S.Qp[s][it] = sMvMI * fl[s];
   }
+  }
   __syncthreads();
 
   // ---- combine: tendency[vid-] -= vMI sM F*  in face order 1..6, then alpha/beta, RK ----
   if (tid < NP) {
+    R acc[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) acc[s] = MI * S.F[0][s][tid] + src[s];
     // a node lies on at most one face per direction: three predicated reads instead of six
     const int it1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
     const int it2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
@@ -692,337 +737,6 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       A.dQ[eoffQ + (size_t)s * NP + tid] = d;
       if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Persistent, software-pipelined variant of the fused tendency kernel (first-order models).
-//
-// The one-shot kernel above is latency-bound: every block first waits a full memory round
-// trip for its face descriptors, then another for the neighbour traces and its own state
-// (ncu: 25 % occupancy, >35 % of issue slots lost to long-scoreboard stalls).  Here a block
-// loops over elements and the loads of element e+1 are issued with cp.async (LDGSTS, no
-// registers, no stall) while element e is being computed:
-//
-//   top of iteration : cp.async.wait_all + barrier B1   (data of e landed; buffers of e-1 free)
-//   after B1         : prefetch group A of e+1 -> other buffer  (own Q, Phi/p_ref, neighbour
-//                      traces, face geometry), using the face descriptors fetched one
-//                      iteration earlier; fetch the descriptors of e+2
-//   volume phase     : fluxes from shared memory -> contravariant fluxes in shared memory
-//   barrier B2       : prefetch group B of e+1 (node geometry, source-term aux) into the single
-//                      buffer the volume phase has just finished reading; issue the dQ loads of e
-//   contraction, face phase (150 items on 5 warps, one item per thread), barrier B3, combine.
-//
-// 160 threads = 4 node warps + 1 warp that takes the face items 128..149, so all warps do one
-// face item.  D stays in registers for the whole kernel.
-// ---------------------------------------------------------------------------------------
-template <class R, int NQ, bool AUX>
-struct PipeSmem {
-  static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
-  struct alignas(16) Stage {
-    alignas(16) R Sg[NFN][4];   // 16-byte cp.async targets first
-    R Q[5][NP];
-    R Qp[5][NFN];
-    R PhiPref[AUX ? 2 : 1][AUX ? NP : 1];
-    R Ap[AUX ? 2 : 1][AUX ? NFN : 1];
-  };
-  Stage st[2];
-  alignas(16) R Geo[NP][10];
-  R Ex[AUX ? 4 : 1][AUX ? NP : 1];   // rho_ref, grad Phi
-  R F[3][5][NP];
-  R P[NP], Rinv[NP];
-  R D[NQ * NQ];
-};
-
-template <class R, int NQ, int NF1, bool AUX>
-__global__ void __launch_bounds__(160, 3)
-dg_tendency_pipe_kernel(const TendArgs<R> A, const AtmosParams<R> P, const int nlaunch) {
-  constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
-  static_assert(NQ == 5, "pipelined kernel is laid out for Nq = 5 (125 nodes, 150 face nodes)");
-  typedef PipeSmem<R, NQ, AUX> SM;
-  typedef typename Vec2<R>::type V2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-
-  const int tid = threadIdx.x;
-  const bool node = tid < NP, item = tid < NFN;
-  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
-  const R *__restrict__ Qg = A.Q;
-  const R *__restrict__ auxg = A.aux;
-
-  if (tid < NQ * NQ) S.D[tid] = A.D[tid];   // visible after the first barrier
-  const int f = item ? tid / NFP : 0, fn = item ? tid - f * NFP : 0;
-  const int fa = fn % NQ, fb = fn / NQ;
-  const int vm = face_to_vol<NQ>(f, fa, fb);
-
-  const int stride = gridDim.x;
-  int idx = blockIdx.x;
-  auto elem_at = [&](int ix) -> int { return A.elems ? A.elems[ix] : ix; };
-  auto conn_of = [&](int e) -> int2 { return item ? A.conn[(size_t)e * 6 + f] : make_int2(0, 0); };
-
-  // group A: everything the face phase and the start of the volume phase need
-  auto prefetch_A = [&](int e, int2 c, int b) {
-    typename SM::Stage &T = S.st[b];
-    if (node) {
-      const size_t o = (size_t)e * 5 * NP + tid;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&T.Q[s][tid], Qg + o + (size_t)s * NP);
-      if (AUX) {
-        const size_t oa = (size_t)e * P.naux * NP + tid;
-        if (P.a_Phi >= 0) cp_async<sizeof(R)>(&T.PhiPref[0][tid], auxg + oa + (size_t)P.a_Phi * NP);
-        if (P.a_ref_p >= 0)
-          cp_async<sizeof(R)>(&T.PhiPref[AUX ? 1 : 0][tid], auxg + oa + (size_t)P.a_ref_p * NP);
-      }
-    }
-    if (item) {
-      const R *sg = A.sgeoP + ((size_t)e * NFN + tid) * 4;
-      cp_async<2 * sizeof(R)>(&T.Sg[tid][0], sg);
-      cp_async<2 * sizeof(R)>(&T.Sg[tid][2], sg + 2);
-      if (((c.y >> 4) & 15) == 0) {
-        const int a = (c.y & 8) ? NQ - 1 - fa : fa;
-        const int vp = face_to_vol<NQ>(c.y & 7, a, fb);
-        const size_t op = (size_t)c.x * 5 * NP + vp;
-#pragma unroll
-        for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&T.Qp[s][tid], Qg + op + (size_t)s * NP);
-        if (AUX) {
-          const size_t oa = (size_t)c.x * P.naux * NP + vp;
-          if (P.a_Phi >= 0) cp_async<sizeof(R)>(&T.Ap[0][tid], auxg + oa + (size_t)P.a_Phi * NP);
-          if (P.a_ref_p >= 0)
-            cp_async<sizeof(R)>(&T.Ap[AUX ? 1 : 0][tid], auxg + oa + (size_t)P.a_ref_p * NP);
-        }
-      }
-    }
-  };
-  // group B: node geometry + source-term aux (single buffer, free after the volume phase)
-  auto prefetch_B = [&](int e) {
-    if (node) {
-      const R *vg = A.vgeoP + ((size_t)e * NP + tid) * 10;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) cp_async<2 * sizeof(R)>(&S.Geo[tid][2 * c], vg + 2 * c);
-      if (AUX) {
-        const size_t oa = (size_t)e * P.naux * NP + tid;
-        if ((P.sources & SRC_GRAVITY) && P.subtract_off)
-          cp_async<sizeof(R)>(&S.Ex[0][tid], auxg + oa + (size_t)P.a_ref_rho * NP);
-        if (P.sources & SRC_GRAVITY) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d)
-            cp_async<sizeof(R)>(&S.Ex[AUX ? 1 + d : 0][tid], auxg + oa + (size_t)(P.a_gradPhi + d) * NP);
-        }
-      }
-    }
-  };
-
-  if (idx >= nlaunch) return;
-  // prologue
-  int e_cur = elem_at(idx);
-  int2 cn_cur = conn_of(e_cur);
-  int e_n1 = (idx + stride < nlaunch) ? elem_at(idx + stride) : -1;
-  int2 cn_n1 = e_n1 >= 0 ? conn_of(e_n1) : make_int2(0, 0);
-  int e_n2 = (idx + 2 * stride < nlaunch) ? elem_at(idx + 2 * stride) : -1;
-  prefetch_A(e_cur, cn_cur, 0);
-  prefetch_B(e_cur);
-  int buf = 0;
-
-  for (; idx < nlaunch; idx += stride, buf ^= 1) {
-    cp_async_wait_all();
-    __syncthreads();  // B1
-    typename SM::Stage &T = S.st[buf];
-    const int e = e_cur;
-    const size_t eoffQ = (size_t)e * 5 * NP;
-    const size_t eoffA = (size_t)e * P.naux * NP;
-    if (e_n1 >= 0) prefetch_A(e_n1, cn_n1, buf ^ 1);
-    // descriptors two elements ahead, element id three ahead
-    int2 cn_n2 = e_n2 >= 0 ? conn_of(e_n2) : make_int2(0, 0);
-    int e_n3 = (idx + 3 * stride < nlaunch) ? elem_at(idx + 3 * stride) : -1;
-
-    // ---- volume: fluxes at my node ----
-    R src[5] = {0, 0, 0, 0, 0};
-    R q[5] = {1, 0, 0, 0, 0};
-    R MI = 0;
-    if (node) {
-#pragma unroll
-      for (int s = 0; s < 5; ++s) q[s] = T.Q[s][tid];
-      const R Phi = (AUX && P.a_Phi >= 0) ? T.PhiPref[0][tid] : R(0);
-      const R pref = (AUX && P.a_ref_p >= 0) ? T.PhiPref[AUX ? 1 : 0][tid] : R(0);
-      const Thermo<R> th = thermo<R>(P, q, Phi);
-      const R pflux = (AUX && P.subtract_off) ? th.p - pref : th.p;
-      S.P[tid] = th.p;
-      S.Rinv[tid] = th.rinv;
-      if (A.aux_out) {
-        A.aux_out[eoffA + (size_t)P.a_theta_v * NP + tid] = th.T / pow_<R>(th.p / P.MSLP, P.kappa);
-        A.aux_out[eoffA + (size_t)P.a_T * NP + tid] = th.T;
-      }
-      const R u[3] = {q[1] * th.rinv, q[2] * th.rinv, q[3] * th.rinv};
-      R F[3][5];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        F[d][0] = q[1 + d];
-        F[d][1] = q[1 + d] * u[0];
-        F[d][2] = q[1 + d] * u[1];
-        F[d][3] = q[1 + d] * u[2];
-        F[d][1 + d] += pflux;
-        F[d][4] = u[d] * (q[4] + th.p);
-      }
-      R g[9];
-      {
-        const V2 *gv = reinterpret_cast<const V2 *>(&S.Geo[tid][0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const V2 x = gv[c];
-          g[2 * c] = x.x;
-          g[2 * c + 1] = x.y;
-        }
-        const V2 x = gv[4];
-        g[8] = x.x;
-        MI = x.y;
-      }
-#pragma unroll
-      for (int m = 0; m < 3; ++m)
-#pragma unroll
-        for (int s = 0; s < 5; ++s)
-          S.F[m][s][tid] = g[3 * m] * F[0][s] + g[3 * m + 1] * F[1][s] + g[3 * m + 2] * F[2][s];
-      if (AUX && (P.sources & SRC_GRAVITY)) {
-        const R rr = P.subtract_off ? q[0] - S.Ex[0][tid] : q[0];
-        src[1] = -rr * S.Ex[AUX ? 1 : 0][tid];
-        src[2] = -rr * S.Ex[AUX ? 2 : 0][tid];
-        src[3] = -rr * S.Ex[AUX ? 3 : 0][tid];
-      }
-      if (P.sources & SRC_CORIOLIS) {
-        src[1] += P.two_Omega * q[2];
-        src[2] -= P.two_Omega * q[1];
-      }
-    }
-    __syncthreads();  // B2
-    if (e_n1 >= 0) prefetch_B(e_n1);
-
-    // old tendency: consumed only in the combine step
-    R dQold[5] = {0, 0, 0, 0, 0};
-    if (node && A.beta != R(0)) {
-#pragma unroll
-      for (int s = 0; s < 5; ++s) dQold[s] = A.dQ[eoffQ + (size_t)s * NP + tid];
-    }
-
-    // ---- volume: weak derivative  MI * D^T (M xi . F) ----
-    R acc[5] = {0, 0, 0, 0, 0};
-    if (node) {
-#pragma unroll
-      for (int n = 0; n < NQ; ++n) {
-        const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
-        const R d1 = S.D[n * NQ + i], d2 = S.D[n * NQ + j], d3 = S.D[n * NQ + k];
-#pragma unroll
-        for (int s = 0; s < 5; ++s)
-          acc[s] += d1 * S.F[0][s][o1] + d2 * S.F[1][s][o2] + d3 * S.F[2][s][o3];
-      }
-#pragma unroll
-      for (int s = 0; s < 5; ++s) acc[s] = MI * acc[s] + src[s];
-    }
-
-    // ---- faces: one face node per thread ----
-    if (item) {
-      const int bctag = (cn_cur.y >> 4) & 15;
-      R n[3], sMvMI;
-      {
-        const V2 *sv = reinterpret_cast<const V2 *>(&T.Sg[tid][0]);
-        const V2 a = sv[0], b = sv[1];
-        n[0] = a.x;
-        n[1] = a.y;
-        n[2] = b.x;
-        sMvMI = b.y;
-      }
-      R qm[5], qp[5];
-#pragma unroll
-      for (int s = 0; s < 5; ++s) qm[s] = T.Q[s][vm];
-      Thermo<R> tm;
-      tm.rinv = S.Rinv[vm];
-      tm.p = S.P[vm];
-      tm.T = tm.p * tm.rinv / P.R_d;
-      const R Phim = (AUX && P.a_Phi >= 0) ? T.PhiPref[0][AUX ? vm : 0] : R(0);
-      const R prefm = (AUX && P.a_ref_p >= 0) ? T.PhiPref[AUX ? 1 : 0][AUX ? vm : 0] : R(0);
-      R Phip = Phim, prefp = prefm;
-      if (bctag == 0) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) qp[s] = T.Qp[s][tid];
-        if (AUX) {
-          if (P.a_Phi >= 0) Phip = T.Ap[0][AUX ? tid : 0];
-          if (P.a_ref_p >= 0) prefp = T.Ap[AUX ? 1 : 0][AUX ? tid : 0];
-        }
-      } else {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) qp[s] = qm[s];
-        const int kind = P.bc_kind[bctag - 1];
-        if (kind == BC_FREESLIP) {
-          const R run = 2 * (qm[1] * n[0] + qm[2] * n[1] + qm[3] * n[2]);
-          qp[1] -= run * n[0];
-          qp[2] -= run * n[1];
-          qp[3] -= run * n[2];
-        } else {
-          qp[1] = -qm[1];
-          qp[2] = -qm[2];
-          qp[3] = -qm[3];
-        }
-      }
-      const Thermo<R> tp = thermo<R>(P, qp, Phip);
-      R fm[5], fp[5], unm, unp;
-      normal_flux<R>(qm, tm.rinv, (AUX && P.subtract_off) ? tm.p - prefm : tm.p, tm.p, n, fm, unm);
-      normal_flux<R>(qp, tp.rinv, (AUX && P.subtract_off) ? tp.p - prefp : tp.p, tp.p, n, fp, unp);
-      R fl[5];
-#pragma unroll
-      for (int s = 0; s < 5; ++s) fl[s] = R(0.5) * (fm[s] + fp[s]);
-      if (NF1 == NF_RUSANOV) {
-        const R cm = sqrt_<R>(P.gamma * tm.p * tm.rinv);
-        const R cp = sqrt_<R>(P.gamma * P.R_d * tp.T);
-        const R lam = R(0.5) * fmax(fabs(unm) + cm, fabs(unp) + cp);
-#pragma unroll
-        for (int s = 0; s < 5; ++s) fl[s] += lam * (qm[s] - qp[s]);
-      } else if (NF1 == NF_ROE) {
-        R diss[5];
-        roe_dissipation<R>(P, n, qm, tm, qp, tp, Phim, diss);
-#pragma unroll
-        for (int s = 0; s < 5; ++s) fl[s] -= diss[s];
-      }
-#pragma unroll
-      for (int s = 0; s < 5; ++s) T.Qp[s][tid] = sMvMI * fl[s];
-    }
-    __syncthreads();  // B3
-
-    // ---- combine ----
-    if (node) {
-      if (i == 0) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][0 * NFP + j + NQ * k];
-      }
-      if (i == NQ - 1) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][1 * NFP + j + NQ * k];
-      }
-      if (j == 0) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][2 * NFP + i + NQ * k];
-      }
-      if (j == NQ - 1) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][3 * NFP + i + NQ * k];
-      }
-      if (k == 0) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][4 * NFP + i + NQ * j];
-      }
-      if (k == NQ - 1) {
-#pragma unroll
-        for (int s = 0; s < 5; ++s) acc[s] -= T.Qp[s][5 * NFP + i + NQ * j];
-      }
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const R d = A.alpha * acc[s] + A.beta * dQold[s];
-        A.dQ[eoffQ + (size_t)s * NP + tid] = d;
-        if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
-      }
-    }
-    e_cur = e_n1;
-    cn_cur = cn_n1;
-    e_n1 = e_n2;
-    cn_n1 = cn_n2;
-    e_n2 = e_n3;
   }
 }
 

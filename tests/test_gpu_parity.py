@@ -128,18 +128,6 @@ def test_multi_gpu_halo_and_parity():
     assert out.stdout.count("MULTI_GPU_PARITY") == 4
 
 
-def test_experimental_pipelined_kernel_matches(monkeypatch):
-    """CMDG_KERNEL=pipe selects the persistent, software-pipelined tendency kernel (kept as an
-    experiment: same results, currently slower than the one-shot kernel)."""
-    monkeypatch.setenv("CMDG_KERNEL", "pipe")
-    res = parity.gcm_case(nf="rusanov", nsteps=2, dt=0.5)
-    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
-    assert res["state_rel_l2"] <= 1e-13, res
-    res = parity.vortex_case(nelem=(4, 4, 2), nf="central", nsteps=2)
-    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
-    assert res["state_rel_l2"] <= 1e-13, res
-
-
 def test_ocean_hbmodel_tendency_and_steps():
     """HBModel (config 5 physics): in-tendency vertical filters, gradient pass with the
     convective-adjustment switch, column integrals, flux-based ocean BCs, LSRK144."""
