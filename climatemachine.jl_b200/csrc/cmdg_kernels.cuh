@@ -297,6 +297,15 @@ __device__ __forceinline__ void prefetch_l2_range(const void *p, size_t bytes, i
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + ((uintptr_t)l << 7)));
 }
 
+// Same with one instruction: bulk L2 prefetch of the 16-byte-aligned part of [p, p+bytes)
+// (one thread issues it; the first/last <16 bytes share a 128-byte line with their neighbours).
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, size_t bytes) {
+  const uintptr_t a0 = ((uintptr_t)p + 15) & ~(uintptr_t)15;
+  const uintptr_t a1 = ((uintptr_t)p + bytes) & ~(uintptr_t)15;
+  if (a1 > a0)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+}
+
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -310,7 +319,12 @@ template <class R, int NQ, bool AUX, bool VISC>
 struct TendSmem {
   static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
   R Q[5][NP];                              // own state
-  R F[3][5][NP];                           // contravariant fluxes  M xi_m . F
+  // contravariant fluxes M xi_m . F.  F12 is read by (k-plane, state) lanes, F3 by (i-plane,
+  // state) lanes; the state stride of F3 is padded to 8 mod 16 + 5 doubles so that both are free of
+  // bank conflicts (k-plane lanes: 25 k + 125 s, i-plane lanes: i + 133 s)
+  static constexpr int NP3 = (NQ == 5) ? 133 : NP;
+  R F12[2][5][NP];
+  R F3[5][NP3];
   R Qp[5][NFN];                            // neighbour traces; reused for the face results
   R P[NP], Rinv[NP];                       // own pressure, 1/rho
   R Phi[AUX ? NP : 1], Pref[AUX ? NP : 1]; // own geopotential, reference pressure
@@ -400,27 +414,30 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   for (int r = 0; r < NITEM; ++r) {
     const int it = ft + r * FSTRIDE;
     cn[r] = (ft >= 0 && it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
+    // face geometry of my items is needed only in the face phase: park it in L1 now
+    if (ft >= 0 && it < NFN)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(A.sgeoP + ((size_t)e * NFN + it) * 4));
   }
 
   // ---- L2 prefetch for the block that will replace this one on the SM: the one-shot kernel
   // is latency-bound (two dependent DRAM round trips per block); with the own-element data
   // already in L2 those become L2 hits and DRAM stays busy during the compute phases ----
-  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x) {
+  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
     const int bn = blockIdx.x + A.pf_dist;
     const int en = A.elems ? A.elems[bn] : bn;
-    prefetch_l2_range<BLOCK>(Qg + (size_t)en * 5 * NP, 5 * NP * sizeof(R), tid);
-    prefetch_l2_range<BLOCK>(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R), tid);
-    prefetch_l2_range<BLOCK>(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R), tid);
-    if (A.beta != R(0)) prefetch_l2_range<BLOCK>(A.dQ + (size_t)en * 5 * NP, 5 * NP * sizeof(R), tid);
+    prefetch_l2_bulk(Qg + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
+    prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R));
+    if (A.beta != R(0)) prefetch_l2_bulk(A.dQ + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
     if (AUX) {
       const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
       const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
       if (lo >= 0 && hi > lo)
-        prefetch_l2_range<BLOCK>(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R), tid);
+        prefetch_l2_bulk(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R));
     }
     if (VISC)
-      prefetch_l2_range<BLOCK>(A.gradflux + (size_t)en * P.ngradflux * NP, (size_t)P.ngradflux * NP * sizeof(R), tid);
-    if (tid == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
+      prefetch_l2_bulk(A.gradflux + (size_t)en * P.ngradflux * NP, (size_t)P.ngradflux * NP * sizeof(R));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
   }
 
   // ---- (b) issue my node's loads ----
@@ -525,7 +542,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     for (int m = 0; m < 3; ++m)
 #pragma unroll
       for (int s = 0; s < 5; ++s)
-        S.F[m][s][tid] = g[3 * m] * F[0][s] + g[3 * m + 1] * F[1][s] + g[3 * m + 2] * F[2][s];
+      {
+        const R v = g[3 * m] * F[0][s] + g[3 * m + 1] * F[1][s] + g[3 * m + 2] * F[2][s];
+        if (m < 2) S.F12[m < 2 ? m : 0][s][tid] = v;
+        else S.F3[s][tid] = v;
+      }
     // sources (tendencies_momentum.jl:66-92); added in the vertical launch in the reference
     if (AUX && (P.sources & SRC_GRAVITY)) {
       const R rr = q[0] - rref;
@@ -565,18 +586,17 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   if (warp == cw) {
     if (lane < NQ * 5) {
+      // (1) lane = (k-plane pk, state ps): xi1 and xi2, result in place of the F12[0] plane
+      // (2) the same lane as (i-plane pk, state ps): xi3, result in place of the F3 plane.
+      // Each plane is read and rewritten by its own lane only: no synchronisation in between.
       const int pk = lane % NQ, ps = lane / NQ;
-      R dk[NQ];
-#pragma unroll
-      for (int n = 0; n < NQ; ++n) dk[n] = const_D<R>(n * NQ + pk);
       R pa[NQ][NQ];
 #pragma unroll
       for (int b = 0; b < NQ; ++b)
 #pragma unroll
         for (int a = 0; a < NQ; ++a) pa[b][a] = R(0);
-      R *F1 = &S.F[0][ps][NQ * NQ * pk];
-      const R *F2 = &S.F[1][ps][NQ * NQ * pk];
-      const R *F3 = &S.F[2][ps][0];
+      R *F1 = &S.F12[0][ps][NQ * NQ * pk];
+      const R *F2 = &S.F12[1][ps][NQ * NQ * pk];
 #pragma unroll
       for (int b = 0; b < NQ; ++b) {
         R f[NQ];
@@ -598,15 +618,25 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
           for (int a = 0; a < NQ; ++a) pa[b][a] += const_D<R>(n * NQ + b) * f[a];
       }
 #pragma unroll
-      for (int n = 0; n < NQ; ++n)
-#pragma unroll
-        for (int b = 0; b < NQ; ++b)
-#pragma unroll
-          for (int a = 0; a < NQ; ++a) pa[b][a] += dk[n] * F3[a + NQ * b + NQ * NQ * n];
-#pragma unroll
       for (int b = 0; b < NQ; ++b)
 #pragma unroll
         for (int a = 0; a < NQ; ++a) F1[a + NQ * b] = pa[b][a];
+      // xi3: out3[j][c] = sum_n D[n][c] F3[i + Nq j + Nq^2 n] in the plane i = pk
+      R *F3 = &S.F3[ps][pk];
+#pragma unroll
+      for (int b = 0; b < NQ; ++b) {
+        R f[NQ], o[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) f[n] = F3[NQ * b + NQ * NQ * n];
+#pragma unroll
+        for (int c = 0; c < NQ; ++c) {
+          o[c] = R(0);
+#pragma unroll
+          for (int n = 0; n < NQ; ++n) o[c] += const_D<R>(n * NQ + c) * f[n];
+        }
+#pragma unroll
+        for (int c = 0; c < NQ; ++c) F3[NQ * b + NQ * NQ * c] = o[c];
+      }
     }
   } else {
   // ---- faces: numerical flux at every face node of this element ----
@@ -714,7 +744,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   if (tid < NP) {
     R acc[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) acc[s] = MI * S.F[0][s][tid] + src[s];
+    for (int s = 0; s < 5; ++s) acc[s] = MI * (S.F12[0][s][tid] + S.F3[s][tid]) + src[s];
     // a node lies on at most one face per direction: three predicated reads instead of six
     const int it1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
     const int it2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
