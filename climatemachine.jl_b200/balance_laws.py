@@ -190,6 +190,10 @@ class HorizontalDirection:
     pass
 
 
+class VerticalDirection:
+    pass
+
+
 @dataclass
 class AtmosModel:
     """Dry, compressible, total-energy AtmosModel (the subset libcmdg compiles in)."""
@@ -352,6 +356,20 @@ def spectral_filter_matrix(r, Nc, σ):
     for n in range(Nc, N + 1):
         Σ[n] = σ((n - Nc) / (N - Nc))
     return (V * Σ[None, :]) @ np.linalg.inv(V)
+
+
+class FilterIndices:
+    """``FilterIndices(I...)`` (Filters.jl:60-98), 1-based state indices as in Julia."""
+
+    def __init__(self, *I):
+        self.I = tuple(int(i) for i in I)
+
+
+class AtmosFilterPerturbations:
+    """``AtmosFilterPerturbations(atmos)`` (src/Atmos/Model/filters.jl:4-48)."""
+
+    def __init__(self, atmos):
+        self.atmos = atmos
 
 
 class CutoffFilter:

@@ -90,6 +90,10 @@ struct cmdg_handle_s {
   std::vector<int64_t> sendrange, recvrange;  // 0-based [first, last) pairs
   void *sendbuf = nullptr, *recvbuf = nullptr;
   size_t commbuf_states = 0;
+  // per-step filter (cmdg_set_step_filter): row-major device copies of the two matrices
+  void *stepWh = nullptr, *stepWv = nullptr, *tmpWh = nullptr, *tmpWv = nullptr;
+  int step_filter_target = -1, step_filter_dir = 0;
+  unsigned step_filter_mask = 0;
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
   bool grid_bound = false;
@@ -504,6 +508,45 @@ int lsrk_update_t(cmdg_handle h, void *dQ, void *Q, double rka, double rkb, doub
   return 0;
 }
 
+// Filters.apply! on real elements; Wh / Wv are row-major device matrices
+template <class R>
+int filter_apply_t(cmdg_handle h, void *Q, int nstate, int target, unsigned mask, const void *Wh,
+                   const void *Wv, int direction, cudaStream_t st) {
+  const int64_t nreal = h->d.nrealelem;
+  if (nreal <= 0) return 0;
+  int a_rho = 0, a_rhoe = 0;
+  if (target == CMDG_FILTER_ATMOS_PERTURBATIONS) {
+    if (h->is_hb || h->d.ref_state != CMDG_REF_HYDROSTATIC || !h->aux || nstate != 5)
+      return fail(h, CMDG_ERR_INVALID, "AtmosFilterPerturbations needs a dry AtmosModel with a HydrostaticState and bound state_auxiliary");
+    const AtmosParams<R> P = make_params<R>(h);
+    a_rho = P.a_ref_rho;
+    a_rhoe = P.a_ref_rho + 3;   // ref_state: rho, p, T, rhoe, ... (ref_state.jl:36-47)
+    mask = 0x1f;
+  }
+  const int do_h = direction != CMDG_DIR_VERTICAL, do_v = direction != CMDG_DIR_HORIZONTAL;
+  if (nstate <= 5)
+    filter_kernel<R, 5, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(
+        (R *)Q, (const R *)h->aux, (const R *)Wh, (const R *)Wv, nstate, h->d.naux, mask, target, a_rho,
+        a_rhoe, do_h, do_v);
+  else
+    return fail(h, CMDG_ERR_UNSUPPORTED, "filter: at most 5 states");
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+// Julia (column-major) Nq x Nq device matrix -> row-major device copy
+template <class R>
+int transpose_small(cmdg_handle h, const void *src_dev, int n, void **dst_dev) {
+  std::vector<R> a(n * n), b(n * n);
+  CU(cudaMemcpy(a.data(), src_dev, a.size() * sizeof(R), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) b[i * n + j] = a[i + n * j];
+  if (!*dst_dev) CU(cudaMalloc(dst_dev, b.size() * sizeof(R)));
+  CU(cudaMemcpy(*dst_dev, b.data(), b.size() * sizeof(R), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 template <class R>
 int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nstage,
                  const double *rka, const double *rkb, const double *rkc, int64_t nsteps,
@@ -559,16 +602,28 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
           if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
           if ((rc = exchange_end_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
         }
+        // a per-step filter changes the new state after the last stage: its halo goes out after
+        // the filter instead of overlapping the interior kernel
+        const bool filt_now = h->step_filter_target >= 0 && s == nstage - 1;
         a.elems = h->exterior;
         if ((rc = launch_tendency<R>(h, a, h->nexterior, st))) return rc;
-        if ((rc = exchange_begin_t<R>(h, nxt, h->d.nstate, st))) return rc;
+        if (!filt_now && (rc = exchange_begin_t<R>(h, nxt, h->d.nstate, st))) return rc;
         a.elems = h->interior;
         if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
-        if ((rc = exchange_end_t<R>(h, nxt, h->d.nstate, st))) return rc;
+        if (!filt_now && (rc = exchange_end_t<R>(h, nxt, h->d.nstate, st))) return rc;
       }
       R *tmp = cur;
       cur = nxt;
       nxt = tmp;
+    }
+    if (h->step_filter_target >= 0 && !h->is_hb) {
+      int rc = filter_apply_t<R>(h, cur, h->d.nstate, h->step_filter_target, h->step_filter_mask,
+                                 h->stepWh, h->stepWv, h->step_filter_dir, st);
+      if (rc) return rc;
+      if (par) {
+        if ((rc = exchange_begin_t<R>(h, cur, h->d.nstate, st))) return rc;
+        if ((rc = exchange_end_t<R>(h, cur, h->d.nstate, st))) return rc;
+      }
     }
   }
   if (cur != (R *)Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
@@ -835,7 +890,7 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV};
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -998,6 +1053,57 @@ int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int3
   if (rc) return rc;
   CU(cudaMemcpyAsync(Q_host, h->Qdev, real, cudaMemcpyDeviceToHost, 0));
   CU(cudaStreamSynchronize(0));
+  return CMDG_OK;
+}
+
+int cmdg_filter_apply(cmdg_handle h, void *Q, int32_t nstate, int32_t target, uint32_t state_mask,
+                      const void *filter_h, const void *filter_v, int32_t direction,
+                      cmdg_stream stream) {
+  if (!h || !Q || !filter_h || !filter_v) return fail(h, CMDG_ERR_INVALID, "cmdg_filter_apply: null argument");
+  if (!h->grid_bound) return fail(h, CMDG_ERR_INVALID, "cmdg_filter_apply before cmdg_bind_grid");
+  if (target != CMDG_FILTER_INDICES && target != CMDG_FILTER_ATMOS_PERTURBATIONS)
+    return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported filter target");
+  if (direction < CMDG_DIR_EVERY || direction > CMDG_DIR_VERTICAL)
+    return fail(h, CMDG_ERR_INVALID, "bad filter direction");
+  if (nstate < 1 || nstate > 5) return fail(h, CMDG_ERR_UNSUPPORTED, "filter: 1..5 states");
+  // matrices arrive in Julia layout: transpose into scratch copies
+  int rc;
+  if (h->fb == 8) {
+    if ((rc = transpose_small<double>(h, filter_h, h->Nq, &h->tmpWh))) return rc;
+    if ((rc = transpose_small<double>(h, filter_v, h->Nq, &h->tmpWv))) return rc;
+    return filter_apply_t<double>(h, Q, nstate, target, state_mask, h->tmpWh, h->tmpWv, direction, (cudaStream_t)stream);
+  }
+  if ((rc = transpose_small<float>(h, filter_h, h->Nq, &h->tmpWh))) return rc;
+  if ((rc = transpose_small<float>(h, filter_v, h->Nq, &h->tmpWv))) return rc;
+  return filter_apply_t<float>(h, Q, nstate, target, state_mask, h->tmpWh, h->tmpWv, direction, (cudaStream_t)stream);
+}
+
+int cmdg_set_step_filter(cmdg_handle h, int32_t target, uint32_t state_mask, const void *filter_h,
+                         const void *filter_v, int32_t direction) {
+  if (!h) return fail(h, CMDG_ERR_INVALID, "null handle");
+  if (target < 0) {
+    h->step_filter_target = -1;
+    return CMDG_OK;
+  }
+  if (h->is_hb) return fail(h, CMDG_ERR_UNSUPPORTED, "per-step filter: AtmosModel handles only");
+  if (!h->grid_bound || !filter_h || !filter_v) return fail(h, CMDG_ERR_INVALID, "cmdg_set_step_filter: bind the grid first and pass both matrices");
+  if (target != CMDG_FILTER_INDICES && target != CMDG_FILTER_ATMOS_PERTURBATIONS)
+    return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported filter target");
+  if (target == CMDG_FILTER_ATMOS_PERTURBATIONS && h->d.ref_state != CMDG_REF_HYDROSTATIC)
+    return fail(h, CMDG_ERR_INVALID, "AtmosFilterPerturbations needs a HydrostaticState reference state");
+  if (direction < CMDG_DIR_EVERY || direction > CMDG_DIR_VERTICAL)
+    return fail(h, CMDG_ERR_INVALID, "bad filter direction");
+  int rc;
+  if (h->fb == 8) {
+    if ((rc = transpose_small<double>(h, filter_h, h->Nq, &h->stepWh))) return rc;
+    if ((rc = transpose_small<double>(h, filter_v, h->Nq, &h->stepWv))) return rc;
+  } else {
+    if ((rc = transpose_small<float>(h, filter_h, h->Nq, &h->stepWh))) return rc;
+    if ((rc = transpose_small<float>(h, filter_v, h->Nq, &h->stepWv))) return rc;
+  }
+  h->step_filter_target = target;
+  h->step_filter_mask = state_mask;
+  h->step_filter_dir = direction;
   return CMDG_OK;
 }
 

@@ -771,6 +771,94 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Filters.apply! (src/Numerics/Mesh/Filters.jl:440-505, kernel_apply_filter! :651-792) as ONE pass
+// over Q: the reference's horizontal launch (xi1, xi2 with filter_matrices[1]) and vertical launch
+// (xi3 with filter_matrices[end]) are fused, the state is read and written once.  Targets:
+// FilterIndices (bit mask of states) and AtmosFilterPerturbations (src/Atmos/Model/filters.jl:4-48:
+// rho - rho_ref, rhoe - rhoe_ref, momentum as is).  Between the two launches the reference adds the
+// reference state back and subtracts it again; that rounding is reproduced.
+// Wh / Wv: row-major [Nq][Nq] (W[i][n] multiplies the value at n).
+// ---------------------------------------------------------------------------------------
+enum { FILTER_TARGET_INDICES = 0, FILTER_TARGET_ATMOS_PERTURBATIONS = 1 };
+template <class R, int NQ, int MAXS>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK)
+filter_kernel(R *__restrict__ Q, const R *__restrict__ aux, const R *__restrict__ Wh,
+              const R *__restrict__ Wv, int nstate, int naux, unsigned mask, int target,
+              int a_ref_rho, int a_ref_rhoe, int do_h, int do_v) {
+  constexpr int NP = Dims<NQ>::NP;
+  __shared__ R s[MAXS][NP];
+  __shared__ R sW[2][NQ * NQ];
+  const int tid = threadIdx.x, e = blockIdx.x;
+  if (tid < NQ * NQ) {
+    sW[0][tid] = Wh[tid];
+    sW[1][tid] = Wv[tid];
+  }
+  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
+  R v[MAXS], ref[MAXS];
+#pragma unroll
+  for (int c = 0; c < MAXS; ++c) v[c] = ref[c] = R(0);
+  if (tid < NP) {
+    const size_t off = (size_t)e * nstate * NP + tid;
+#pragma unroll
+    for (int c = 0; c < MAXS; ++c)
+      if (c < nstate && ((mask >> c) & 1u)) v[c] = Q[off + (size_t)c * NP];
+    if (target == FILTER_TARGET_ATMOS_PERTURBATIONS) {
+      const size_t oa = (size_t)e * naux * NP + tid;
+      ref[0] = aux[oa + (size_t)a_ref_rho * NP];
+      if (MAXS > 4) ref[MAXS > 4 ? 4 : 0] = aux[oa + (size_t)a_ref_rhoe * NP];
+    }
+#pragma unroll
+    for (int c = 0; c < MAXS; ++c) {
+      v[c] -= ref[c];
+      s[c][tid] = v[c];
+    }
+  }
+  __syncthreads();
+  // three tensor-product sweeps; sweep d contracts along xi_{d+1}
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const bool on = d < 2 ? do_h : do_v;
+    if (!on) continue;
+    if (d == 2 && do_h) {
+      // boundary between the reference's two launches: result(+ref) then argument(-ref)
+      if (tid < NP) {
+#pragma unroll
+        for (int c = 0; c < MAXS; ++c) s[c][tid] = (v[c] + ref[c]) - ref[c];
+      }
+      __syncthreads();
+    }
+    const R *W = sW[d < 2 ? 0 : 1];
+    const int me = d == 0 ? i : (d == 1 ? j : k);
+    const int stride = d == 0 ? 1 : (d == 1 ? NQ : NQ * NQ);
+    const int base = tid - me * stride;
+    if (tid < NP) {
+#pragma unroll
+      for (int c = 0; c < MAXS; ++c) v[c] = R(0);
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) {
+        const R w = W[me * NQ + n];
+#pragma unroll
+        for (int c = 0; c < MAXS; ++c) v[c] += w * s[c][base + n * stride];
+      }
+    }
+    __syncthreads();   // every read of s in this sweep is done
+    if (d == 0) {
+      if (tid < NP) {
+#pragma unroll
+        for (int c = 0; c < MAXS; ++c) s[c][tid] = v[c];
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < NP) {
+    const size_t off = (size_t)e * nstate * NP + tid;
+#pragma unroll
+    for (int c = 0; c < MAXS; ++c)
+      if (c < nstate && ((mask >> c) & 1u)) Q[off + (size_t)c * NP] = v[c] + ref[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Gradient pass: volume_gradients! H/V (DGModel_kernels.jl:934-1328) +
 // dgsem_interface_gradients! (:1365-1651) with CentralNumericalFluxGradient
 // (NumericalFluxes.jl:65-123), fused per element.  Writes the gradient-flux array.

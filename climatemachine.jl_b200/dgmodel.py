@@ -290,6 +290,38 @@ class DGModel:
         _lib.check(L.cmdg_exchange_end(self._h, _ptr(arr.data), arr.nstate, st), self._h)
         torch.cuda.current_stream().synchronize()
 
+    # -- Filters.apply!(Q, target, grid, filter; state_auxiliary, direction) ------------------
+    def _filter_args(self, target, filter, direction):
+        if isinstance(target, bl.AtmosFilterPerturbations):
+            kind, mask = _lib.FILTER_ATMOS_PERTURBATIONS, 0x1f
+        elif isinstance(target, bl.FilterIndices):
+            kind, mask = _lib.FILTER_INDICES, sum(1 << (i - 1) for i in target.I)
+        else:
+            raise bl.UnsupportedModelError(f"filter target {type(target).__name__} is not supported")
+        if not hasattr(filter, "filter_matrix"):
+            raise bl.UnsupportedModelError(f"filter {type(filter).__name__} is not supported")
+        d = {bl.EveryDirection: _lib.DIR_EVERY, bl.HorizontalDirection: _lib.DIR_HORIZONTAL,
+             bl.VerticalDirection: _lib.DIR_VERTICAL}[type(direction or bl.EveryDirection())]
+        # device copy in Julia (column-major) memory order, as filter.filter_matrices[i] is
+        W = torch.as_tensor(np.ascontiguousarray(np.asarray(filter.filter_matrix).T)).to(self.grid.device).to(self.grid.FT)
+        return kind, mask, W, d
+
+    def apply_filter(self, Q, target, filter, direction=None):
+        kind, mask, W, d = self._filter_args(target, filter, direction)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cmdg_filter_apply(self._h, _ptr(Q.data), Q.nstate, kind, mask, _ptr(W),
+                                                _ptr(W), d, st), self._h)
+        torch.cuda.current_stream().synchronize()
+
+    def set_step_filter(self, target, filter=None, direction=None):
+        """Per-step `cbfilter` callback of the GCM drivers, run inside cmdg_lsrk_steps
+        (``target=None`` removes it)."""
+        if target is None:
+            _lib.check(_lib.lib().cmdg_set_step_filter(self._h, -1, 0, None, None, 0), self._h)
+            return
+        kind, mask, W, d = self._filter_args(target, filter, direction)
+        _lib.check(_lib.lib().cmdg_set_step_filter(self._h, kind, mask, _ptr(W), _ptr(W), d), self._h)
+
     def set_timing(self, enable=True):
         _lib.check(_lib.lib().cmdg_set_timing(self._h, int(enable)), self._h)
 

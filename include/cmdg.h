@@ -220,6 +220,31 @@ int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int3
                          const double *rkc_host, int64_t nsteps);
 
 /*
+ * Replaces `Filters.apply!(Q, target, grid, filter; state_auxiliary, direction)`,
+ * src/Numerics/Mesh/Filters.jl:440-505 (kernel_apply_filter!, :651-792), on real elements, as one
+ * pass over Q.  target: CMDG_FILTER_INDICES = FilterIndices(I...) with `state_mask` bit s-1 set for
+ * every filtered state s; CMDG_FILTER_ATMOS_PERTURBATIONS = AtmosFilterPerturbations(atmos)
+ * (src/Atmos/Model/filters.jl:4-48; needs a HydrostaticState reference state in the bound
+ * state_auxiliary).  filter_h / filter_v: `filter.filter_matrices[1]` / `[end]`, Nq x Nq device
+ * arrays in Julia layout.  direction: CMDG_DIR_EVERY, CMDG_DIR_HORIZONTAL or CMDG_DIR_VERTICAL.
+ */
+enum { CMDG_FILTER_INDICES = 0, CMDG_FILTER_ATMOS_PERTURBATIONS = 1 };
+enum { CMDG_DIR_VERTICAL = 2 };
+int cmdg_filter_apply(cmdg_handle h, void *Q, int32_t nstate, int32_t target, uint32_t state_mask,
+                      const void *filter_h, const void *filter_v, int32_t direction,
+                      cmdg_stream stream);
+/*
+ * Registers a filter that cmdg_lsrk_steps / cmdg_lsrk_steps_host apply to Q after every completed
+ * step -- the per-step `cbfilter` callback of the GCM drivers
+ * (experiments/TestCase/baroclinic_wave.jl:265-277, tutorials/Atmos/heldsuarez.jl:256-268:
+ * GenericCallbacks.EveryXSimulationSteps(1) do Filters.apply!(Q, AtmosFilterPerturbations(model),
+ * grid, ExponentialFilter(grid, 0, order); state_auxiliary) end).  target < 0 removes it.  The
+ * matrices are copied.
+ */
+int cmdg_set_step_filter(cmdg_handle h, int32_t target, uint32_t state_mask, const void *filter_h,
+                         const void *filter_v, int32_t direction);
+
+/*
  * Halo exchange of MPIStateArray face data, src/Arrays/MPIStateArrays.jl:411-514:
  * cmdg_comm_unique_id fills a 128-byte ncclUniqueId on one rank; the caller broadcasts it
  * (MPI in Julia, torch.distributed in the Python harness); cmdg_comm_init joins the

@@ -231,6 +231,55 @@ def heldsuarez_case(nf="rusanov", nsteps=1, dt=0.5, turbulence=("smagorinsky", 0
                         diffusion_direction=diffusion_direction, skip_zero_viscosity=False)
 
 
+def filter_case(direction="every", target="indices", nsteps=0, dt=0.5):
+    """Filters.apply! parity: FilterIndices(1, 3, 5) / AtmosFilterPerturbations on a perturbed
+    baroclinic-wave state (cubed sphere, ExponentialFilter(grid, 0, 10) as the GCM drivers use);
+    with nsteps > 0 also the per-step filter inside the fused stepper (cbfilter callback)."""
+    import types
+    from oracle import filters as ofilters
+    P = pkg()
+    model, gs = gcm_setup(3, 2)
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], "rusanov", skip_zero_viscosity=True)
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_baroclinic_wave(model, aux)
+    rng = np.random.default_rng(1)
+    Q0 = Q0 * (1 + 1e-3 * rng.standard_normal(Q0.shape))
+    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
+    W = ofilters.exponential_filter_matrix(g.xi[0], 0, 10)
+    dg, dgrid = make_device_dg(odgm, g, "rusanov", skip_zero_viscosity=True)
+    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    filt = types.SimpleNamespace(filter_matrix=W)
+    if target == "indices":
+        otarget, dtarget = ofilters.FilterIndices(0, 2, 4), P.FilterIndices(1, 3, 5)
+    else:
+        otarget, dtarget = ofilters.AtmosFilterPerturbations(model), P.AtmosFilterPerturbations(dg.balance_law)
+    ddir = {"every": P.EveryDirection, "horizontal": P.HorizontalDirection, "vertical": P.VerticalDirection}[direction]()
+    res = {}
+    if nsteps == 0:
+        before = oQ.data.copy()
+        ofilters.apply(oQ.data, otarget, g, W, state_auxiliary=odgm.state_auxiliary[0].data, direction=direction)
+        dg.apply_filter(dQ, dtarget, filt, ddir)
+        got = dQ.realdata.cpu().numpy()
+        res["filtered_rel_l2"] = rel_l2(got, oQ.realdata)
+        # relative to what the filter changed (the perturbation), not to the O(1) state
+        res["change_rel_l2"] = rel_l2(got - before[:g.nreal], oQ.realdata - before[:g.nreal])
+    else:
+        osol = oode.LSRK54CarpenterKennedy(odgm, [oQ], dt=dt, t0=0.0)
+        for _ in range(nsteps):
+            oode.solve([oQ], osol, numberofsteps=1)
+            ofilters.apply(oQ.data, otarget, g, W, state_auxiliary=odgm.state_auxiliary[0].data, direction=direction)
+            omsa.ghost_exchange([oQ])
+        dg.set_step_filter(dtarget, filt, ddir)
+        dsol = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt, t0=0.0)
+        P.solve(dQ, dsol, numberofsteps=nsteps)
+        res["state_rel_l2"] = rel_l2(dQ.realdata.cpu().numpy(), oQ.realdata)
+    res["launches"] = dg.kernel_launches()
+    dg.close()
+    return res
+
+
 def box_setup(nelem=(3, 2, 3), FT=np.float64, turbulence=("smagorinsky", 0.21), csize=1,
               periodic_z=False):
     """LES-like box (tutorials/Atmos/risingbubble.jl without tracers): flat orientation,

@@ -110,6 +110,23 @@ def test_held_suarez_forcing_and_sponge(turbulence):
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+@pytest.mark.parametrize("direction", ["every", "horizontal", "vertical"])
+@pytest.mark.parametrize("target", ["indices", "atmos_perturbations"])
+def test_filters_apply(direction, target):
+    """Filters.apply! with FilterIndices / AtmosFilterPerturbations, fused into one
+    pass over Q (the reference launches a horizontal and a vertical kernel)."""
+    res = parity.filter_case(direction=direction, target=target)
+    assert res["filtered_rel_l2"] <= 1e-14, res
+    assert res["change_rel_l2"] <= 1e-10, res
+
+
+def test_per_step_filter_in_fused_stepper():
+    """cbfilter of the GCM drivers (EveryXSimulationSteps(1)): LSRK54 steps with the exponential
+    filter applied to the perturbations after every step, inside cmdg_lsrk_steps."""
+    res = parity.filter_case(direction="every", target="atmos_perturbations", nsteps=3)
+    assert res["state_rel_l2"] <= 1e-12, res
+
+
 def test_multi_gpu_halo_and_parity():
     """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU box skips it, `gpurun --gpus 2` runs it)."""
     import os
