@@ -69,7 +69,8 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.idx), "-lms", os.environ.get("BENCH_SMI_MS", "20")],
+                stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -229,7 +230,7 @@ def run_b200(args):
             break
         sol.dostep(Q, 0.0, nsteps=5)
         torch.cuda.synchronize()
-    dg.set_timing(True)
+    dg.set_timing(not os.environ.get("BENCH_NO_KERNEL_TIMING"))
     l0 = dg.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
