@@ -42,6 +42,16 @@ def algorithmic_bytes_per_node(workload):
         b_eval = w * (3 * S + 11 + A_vol) + 1.2 * (w * (5 + S + A_face) + 8) + w * GFu + 1.2 * w * GFu
         b_stage = b_eval + w * S
         return b_eval, (13 * b_stage + (b_stage - w * S)) / 14
+    if workload == "held_suarez":
+        # Euler part + gradient pass + gradient-flux reads in the tendency pass.
+        # Tendency launch only (the roofline kernel): A_vol = Phi, grad Phi, rho_ref, p_ref, Delta,
+        # coord (HS latitude) = 10; A_face = Phi, p_ref, Delta, grad Phi = 6 ... the formula of 8(d).
+        S, GF = 5, 10
+        b_tend = w * (3 * S + 11 + 10) + 1.2 * (w * (5 + S + 6) + 8) + w * GF + 1.2 * w * GF
+        b_grad = w * (S + 2 + 9 + GF) + 1.2 * (w * (5 + S + 2) + 8)
+        b_stage = b_tend + w * S
+        # returned pair: (whole evaluation incl. gradient pass, tendency launch averaged over stages)
+        return b_tend + b_grad, (4 * b_stage + (b_stage - w * S)) / 5
     if workload == "baroclinic_wave":
         S, A_vol, A_face = 5, 6, 2
     else:  # isentropic vortex, Euler-minimal
@@ -118,11 +128,26 @@ def build_case(P, workload, ne, nvert, rank, nranks, device):
     import numpy as np
     import torch
     from climatemachine_jl_b200 import topologies as tp, grids as gr, atmos_init as ai
-    if workload == "baroclinic_wave":
+    if workload in ("baroclinic_wave", "held_suarez"):
         ps = P.EarthParameterSet()
         R = np.linspace(ps.planet_radius, ps.planet_radius + 30e3, nvert + 1)
         topo = tp.stacked_cubed_sphere_topology(ne, R, (1, 2), rank, nranks)
         grid = gr.build_grid(topo, 4, torch.float64, tp.cubed_sphere_warp, device)
+        if workload == "held_suarez":
+            # BASELINE.json configs[3] as tutorials/Atmos/heldsuarez.jl:160-201 sets it, explicit
+            # LSRK54, hyperdiffusion off: Smagorinsky(0.21), horizontal diffusion direction,
+            # Gravity + Coriolis + HeldSuarezForcing + RayleighSponge(30 km, 12 km, 1/900 s)
+            model = P.AtmosModel(orientation=P.SphericalOrientation(),
+                                 ref_state=P.HydrostaticState(P.DecayingTemperatureProfile(290.0, 220.0, 8e3)),
+                                 turbulence=P.SmagorinskyLilly(0.21),
+                                 source=(P.Gravity(), P.Coriolis(), P.HeldSuarezForcing(),
+                                         P.RayleighSponge(30e3, 12e3, 1 / 60 / 15, (0.0, 0.0, 0.0), 2.0)),
+                                 boundaryconditions=(P.AtmosBC(), P.AtmosBC()))
+            aux = P.MPIStateArray(grid, model.number_states("Auxiliary"))
+            dg = P.DGModel(model, grid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                           P.CentralNumericalFluxGradient(), state_auxiliary=aux,
+                           diffusion_direction=P.HorizontalDirection(), write_aux_diagnostics=True)
+            return dict(topo=topo, grid=grid, model=model, dg=dg, aux=aux, dt=0.4, ai=ai)
         model = P.AtmosModel(orientation=P.SphericalOrientation(),
                              ref_state=P.HydrostaticState(P.DecayingTemperatureProfile(290.0, 220.0, 8e3)),
                              turbulence=P.ConstantKinematicViscosity(0.0),
@@ -178,7 +203,8 @@ def run_b200(args):
         if args.nvert == 10:
             args.nvert = 50
     else:
-        ne = args.ne or (WEAK_NE.get(world, int(round(32 * world ** 0.5))) if args.workload == "baroclinic_wave"
+        ne = args.ne or (WEAK_NE.get(world, int(round(32 * world ** 0.5)))
+                         if args.workload in ("baroclinic_wave", "held_suarez")
                          else int(round(64 * world ** (1 / 3))))
     case = build_case(P, args.workload, ne, args.nvert, rank, world, dev)
     dg, grid, model, ai = case["dg"], case["grid"], case["model"], case["ai"]
@@ -197,7 +223,9 @@ def run_b200(args):
         ex = (lambda arr: dg.ghost_exchange(arr)) if world > 1 else None
         aux0 = ai.init_state_auxiliary(model, grid, exchange=ex)
         case["aux"].data.copy_(aux0.data)
-        if args.workload == "baroclinic_wave":
+        if args.workload in ("baroclinic_wave", "held_suarez"):
+            # (Held-Suarez starts from rest + noise in the tutorial; the baroclinic-wave state gives
+            # the friction, relaxation and sponge terms something to act on -- synthetic either way)
             Q.data[:grid.nrealelem] = ai.baroclinic_wave(model, grid, case["aux"])
         else:
             Q.data[:grid.nrealelem] = ai.isentropic_vortex(model, grid, 0.0)
@@ -307,13 +335,17 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": (f"dry baroclinic wave, cubed sphere ne={ne} x {args.nvert} vertical, N=4, "
                                 "Rusanov, LSRK54, dt=0.4 s" if args.workload == "baroclinic_wave"
+                                else f"Held-Suarez dry GCM + SmagorinskyLilly(0.21) (gradient pass + viscous fluxes, horizontal "
+                                f"diffusion direction), sources Gravity/Coriolis/HeldSuarezForcing/RayleighSponge, cubed sphere "
+                                f"ne={ne} x {args.nvert}, N=4, Rusanov, LSRK54, dt=0.4 s, hyperdiffusion off"
+                                if args.workload == "held_suarez"
                                 else f"OceanBoxGCM HBModel ocean gyre, {ne * world}x{ne}x{args.nvert} elements, N=4, "
                                 "Rusanov, LSRK144 (a step = 14 stages), dt=55 s" if ocean
                                 else f"isentropic vortex, periodic box {ne}^3, N=4, Rusanov, LSRK54"),
                    "nelem_total": int(nodes / NP), "dof_total": int(dof),
                    "cache": "inputs larger than L2 (Q+dQ+Qout+aux+geometry = %.0f MB per GPU vs 126 MB L2)"
                             % (nodes_local * 8 * (3 * NSTATE + case["aux"].nstate + 10 + 4.8 + (10 if ocean else 0)) / 1e6),
-                   "skip_zero_viscosity": not ocean, "parallelism": f"element partition x{world}"},
+                   "skip_zero_viscosity": not ocean and args.workload != "held_suarez", "parallelism": f"element partition x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "hb_tendency_kernel<double,5,RUSANOV>" if ocean else "dg_tendency_kernel<double,5,RUSANOV,...>",
@@ -328,7 +360,7 @@ def run_b200(args):
         "clocks": clk,
         "norm_ratio": norm1 / norm0,
     }
-    if world == 1 and not args.no_cpu_baseline and not ocean:
+    if world == 1 and not args.no_cpu_baseline and not ocean and args.workload != "held_suarez":
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -431,7 +463,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex", "ocean_gyre"])
+    ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex", "ocean_gyre", "held_suarez"])
     ap.add_argument("--ne", type=int, default=0, help="horizontal elements per cube edge / box edge")
     ap.add_argument("--nvert", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

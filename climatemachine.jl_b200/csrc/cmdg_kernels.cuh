@@ -178,15 +178,25 @@ __device__ __forceinline__ void flux_second_order(const AtmosParams<R> &P, const
     R norm2 = S[0][0] * S[0][0] + 2 * S[1][0] * S[1][0] + 2 * S[2][0] * S[2][0] +
               S[1][1] * S[1][1] + 2 * S[2][1] * S[2][1] + S[2][2] * S[2][2];
     R normS = sqrt_<R>(2 * norm2);
-    R k[3] = {gradPhi[0] / P.grav, gradPhi[1] / P.grav, gradPhi[2] / P.grav};
-    // eps(normS): spacing of floating point numbers at normS
+    const R ig = R(1) / P.grav;   // uniform: one division per call instead of three
+    R k[3] = {gradPhi[0] * ig, gradPhi[1] * ig, gradPhi[2] * ig};
+    // eps(normS): spacing of floating point numbers at normS (Julia's eps(x)), from the exponent
+    // bits for normal numbers, nextafter otherwise
     R epsn;
     if (sizeof(R) == 8) {
-      double x = fabs((double)normS);
-      epsn = (R)(x == 0.0 ? 4.9406564584124654e-324 : (nextafter(x, 1.0e308 * 10) - x));
+      const double x = fabs((double)normS);
+      const long long eb = __double_as_longlong(x) & 0x7ff0000000000000LL;
+      if (eb > (53LL << 52) && eb < 0x7ff0000000000000LL)
+        epsn = (R)__longlong_as_double(eb - (52LL << 52));
+      else
+        epsn = (R)(x == 0.0 ? 4.9406564584124654e-324 : (nextafter(x, 1.0e308 * 10) - x));
     } else {
-      float x = fabsf((float)normS);
-      epsn = (R)(x == 0.0f ? 1.4012984643e-45f : (nextafterf(x, 3.0e38f * 10) - x));
+      const float x = fabsf((float)normS);
+      const int eb = __float_as_int(x) & 0x7f800000;
+      if (eb > (24 << 23) && eb < 0x7f800000)
+        epsn = (R)__int_as_float(eb - (23 << 23));
+      else
+        epsn = (R)(x == 0.0f ? 1.4012984643e-45f : (nextafterf(x, 3.0e38f * 10) - x));
     }
     R Ri = gf[9] / (normS * normS + epsn);
     R fb = R(1) - Ri * P.inv_Pr_turb;
@@ -339,6 +349,9 @@ struct TendSmem {
 template <class R> __device__ __forceinline__ R log_(R x);
 template <> __device__ __forceinline__ double log_(double x) { return log(x); }
 template <> __device__ __forceinline__ float log_(float x) { return logf(x); }
+template <class R> __device__ __forceinline__ R exp_(R x);
+template <> __device__ __forceinline__ double exp_(double x) { return exp(x); }
+template <> __device__ __forceinline__ float exp_(float x) { return expf(x); }
 template <class R> __device__ __forceinline__ R sinpi_(R x);
 template <> __device__ __forceinline__ double sinpi_(double x) { return sinpi(x); }
 template <> __device__ __forceinline__ float sinpi_(float x) { return sinpif(x); }
@@ -355,11 +368,12 @@ __device__ __forceinline__ void extended_sources(const AtmosParams<R> &P, const 
     const R s2 = x[2] * x[2] / (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);  // sin^2(lat)
     const R c2 = R(1) - s2;
     const R sigma = th.p / P.MSLP;
-    const R exner = pow_<R>(sigma, P.kappa);
+    const R lsig = log_<R>(sigma);
+    const R exner = exp_<R>(P.kappa * lsig);   // sigma^kappa with the logarithm shared with T_eq
     const R sigma_b = R(7) / R(10);
     const R dsig = (sigma - sigma_b) / (R(1) - sigma_b);
     const R hf = dsig > R(0) ? dsig : R(0);
-    R T_eq = (R(315) - R(60) * s2 - R(10) * log_<R>(sigma) * c2) * exner;
+    R T_eq = (R(315) - R(60) * s2 - R(10) * lsig * c2) * exner;
     T_eq = T_eq > R(200) ? T_eq : R(200);
     const R k_T = k_a + (k_s - k_a) * hf * (c2 * c2);
     const R k_v = k_f * hf;
@@ -651,6 +665,21 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
     R n[3], sMvMI;
     load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
+    // Smagorinsky needs grad Phi and Delta of both sides at the face node: issue these (L2) loads
+    // now so that their latency hides behind the first-order flux
+    R gPm[3] = {0, 0, 0}, gPp[3] = {0, 0, 0}, Dm = 0, Dp = 0;
+    if (VISC && bctag == 0 && P.turbulence == TURB_SMAGORINSKY) {
+      const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
+      const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
+      const size_t om = eoffA + vm, op = (size_t)c.x * P.naux * NP + vp;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        gPm[d] = auxg[om + (size_t)(P.a_gradPhi + d) * NP];
+        gPp[d] = auxg[op + (size_t)(P.a_gradPhi + d) * NP];
+      }
+      Dm = auxg[om + (size_t)P.a_Delta * NP];
+      Dp = auxg[op + (size_t)P.a_Delta * NP];
+    }
     R qm[5], qp[5];
 #pragma unroll
     for (int s = 0; s < 5; ++s) qm[s] = S.Q[s][vm];
@@ -711,19 +740,6 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < NGF; ++s) {
         gfm[s] = S.GF[VISC ? s : 0][VISC ? vm : 0];
         gfp[s] = (s < P.ngradflux) ? S.GFp[VISC ? s : 0][VISC ? it : 0] : R(0);
-      }
-      R gPm[3] = {0, 0, 0}, gPp[3] = {0, 0, 0}, Dm = 0, Dp = 0;
-      if (P.turbulence == TURB_SMAGORINSKY) {
-        const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
-        const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
-        const size_t om = eoffA + vm, op = (size_t)c.x * P.naux * NP + vp;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          gPm[d] = auxg[om + (size_t)(P.a_gradPhi + d) * NP];
-          gPp[d] = auxg[op + (size_t)(P.a_gradPhi + d) * NP];
-        }
-        Dm = auxg[om + (size_t)P.a_Delta * NP];
-        Dp = auxg[op + (size_t)P.a_Delta * NP];
       }
       R F2m[3][5], F2p[3][5];
       flux_second_order<R>(P, qm, gfm, gPm, Dm, F2m);

@@ -23,10 +23,21 @@ for ln in open(sass):
     if m:
         line_of[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(src_csv)))
+# the export holds one table per profiled launch: take the LAST launch whose kernel name contains
+# $NCU_KERNEL (default: the last table)
+import os
+want = os.environ.get("NCU_KERNEL", "")
+tables, name = [], ""
 for i, r in enumerate(rows):
+    if r and r[0] == "Kernel Name":
+        name = r[1]
     if "Address" in r and "Source" in r:
-        hdr, start = r, i + 1
-        break
+        tables.append((name, i))
+sel = [t for t in tables if want in t[0]] or tables
+hdr, start = rows[sel[-1][1]], sel[-1][1] + 1
+end = min([t[1] for t in tables if t[1] > sel[-1][1]] + [len(rows)])
+rows = rows[:end]
+print("kernel:", sel[-1][0][:100])
 ix = {n: i for i, n in enumerate(hdr)}
 base = None
 agg = defaultdict(lambda: defaultdict(float))
