@@ -16,6 +16,7 @@ SRC_GRAVITY, SRC_CORIOLIS, SRC_HELD_SUAREZ, SRC_RAYLEIGH_SPONGE = 1, 2, 4, 8
 BC_FREESLIP, BC_NOSLIP = 1, 2
 DIR_EVERY, DIR_HORIZONTAL, DIR_VERTICAL = 0, 1, 2
 FILTER_INDICES, FILTER_ATMOS_PERTURBATIONS = 0, 1
+COURANT_ADVECTIVE, COURANT_NONDIFFUSIVE, COURANT_DIFFUSIVE = 0, 1, 2
 
 ERRORS = {-1: "CMDG_ERR_INVALID", -2: "CMDG_ERR_UNSUPPORTED", -3: "CMDG_ERR_CUDA",
           -4: "CMDG_ERR_NCCL", -5: "CMDG_ERR_NODEVICE"}
@@ -68,7 +69,7 @@ SYMBOLS = [
     "cmdg_lsrk_steps_host", "cmdg_comm_unique_id", "cmdg_comm_init", "cmdg_exchange_begin",
     "cmdg_exchange_end", "cmdg_sync", "cmdg_kernel_launches", "cmdg_set_timing",
     "cmdg_last_kernel_ms", "cmdg_set_ocean_model", "cmdg_bind_ocean_operators",
-    "cmdg_filter_apply", "cmdg_set_step_filter",
+    "cmdg_filter_apply", "cmdg_set_step_filter", "cmdg_courant",
 ]
 
 
@@ -101,6 +102,7 @@ def lib():
                                        C.POINTER(dbl), i64]
     L.cmdg_filter_apply.argtypes = [vp, vp, i32, i32, C.c_uint32, vp, vp, i32, vp]
     L.cmdg_set_step_filter.argtypes = [vp, i32, C.c_uint32, vp, vp, i32]
+    L.cmdg_courant.argtypes = [vp, vp, vp, dbl, i32, i32, C.POINTER(dbl), vp]
     L.cmdg_comm_unique_id.argtypes = [vp]
     L.cmdg_comm_init.argtypes = [vp, vp, i32, i32]
     L.cmdg_exchange_begin.argtypes = [vp, vp, i32, vp]

@@ -91,6 +91,7 @@ struct cmdg_handle_s {
   void *sendbuf = nullptr, *recvbuf = nullptr;
   size_t commbuf_states = 0;
   // per-step filter (cmdg_set_step_filter): row-major device copies of the two matrices
+  void *courant_dev = nullptr;
   void *stepWh = nullptr, *stepWv = nullptr, *tmpWh = nullptr, *tmpWv = nullptr;
   int step_filter_target = -1, step_filter_dir = 0;
   unsigned step_filter_mask = 0;
@@ -890,7 +891,7 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv};
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -1104,6 +1105,46 @@ int cmdg_set_step_filter(cmdg_handle h, int32_t target, uint32_t state_mask, con
   h->step_filter_target = target;
   h->step_filter_mask = state_mask;
   h->step_filter_dir = direction;
+  return CMDG_OK;
+}
+
+int cmdg_courant(cmdg_handle h, const void *Q, const void *vgeo, double dt, int32_t kind,
+                 int32_t direction, double *result_host, cmdg_stream stream) {
+  if (!h || !Q || !vgeo || !result_host) return fail(h, CMDG_ERR_INVALID, "cmdg_courant: null argument");
+  if (h->is_hb) return fail(h, CMDG_ERR_UNSUPPORTED, "cmdg_courant: AtmosModel handles only");
+  if (int rc = check_ready(h)) return rc;
+  if (kind < CMDG_COURANT_ADVECTIVE || kind > CMDG_COURANT_DIFFUSIVE)
+    return fail(h, CMDG_ERR_INVALID, "bad courant kind");
+  if (direction < CMDG_DIR_EVERY || direction > CMDG_DIR_VERTICAL)
+    return fail(h, CMDG_ERR_INVALID, "bad direction");
+  if (kind == CMDG_COURANT_DIFFUSIVE && !h->gradflux)
+    return fail(h, CMDG_ERR_INVALID, "diffusive courant needs the bound state_gradient_flux");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->courant_dev) CU(cudaMalloc(&h->courant_dev, sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(h->courant_dev, 0, sizeof(unsigned long long), st));
+  const int64_t nreal = h->d.nrealelem;
+  if (nreal > 0) {
+    if (h->fb == 8) {
+      const AtmosParams<double> P = make_params<double>(h);
+      courant_kernel<double, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(
+          (const double *)Q, (const double *)h->aux, (const double *)h->gradflux, (const double *)vgeo, P,
+          dt, kind, direction, (unsigned long long *)h->courant_dev);
+    } else {
+      const AtmosParams<float> P = make_params<float>(h);
+      courant_kernel<float, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(
+          (const float *)Q, (const float *)h->aux, (const float *)h->gradflux, (const float *)vgeo, P,
+          (float)dt, kind, direction, (unsigned long long *)h->courant_dev);
+    }
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  unsigned long long bits = 0;
+  CU(cudaMemcpyAsync(&bits, h->courant_dev, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  double v;
+  memcpy(&v, &bits, sizeof(v));
+  // typemin for a rank without real elements (SpaceDiscretization.jl:359-361)
+  *result_host = nreal > 0 ? v : -INFINITY;
   return CMDG_OK;
 }
 

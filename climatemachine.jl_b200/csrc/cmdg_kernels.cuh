@@ -168,12 +168,12 @@ __device__ __forceinline__ void normal_flux(const R q[5], R rinv, R pflux, R p, 
 // Second-order (diffusive) flux F2[d][s] of the dry AtmosModel
 // (tendencies_momentum.jl:36-43, tendencies_energy.jl:27-59, TurbulenceClosures.jl:364-499).
 // gf: grad h_tot[3], S11,S21,S31,S22,S32,S33, [N2]
+// Diagonal of the turbulent viscosity tensor nu (turbulence_tensors, TurbulenceClosures.jl:368-404
+// constant, :472-499 Smagorinsky-Lilly with the buoyancy correction).
 template <class R>
-__device__ __forceinline__ void flux_second_order(const AtmosParams<R> &P, const R q[5],
-                                                  const R *gf, const R gradPhi[3], R Delta,
-                                                  R F2[3][5]) {
+__device__ __forceinline__ void turbulence_nu(const AtmosParams<R> &P, const R q[5], const R *gf,
+                                              const R gradPhi[3], R Delta, R nu[3]) {
   const R S[3][3] = {{gf[3], gf[4], gf[5]}, {gf[4], gf[6], gf[7]}, {gf[5], gf[7], gf[8]}};
-  R nu[3];
   if (P.turbulence == TURB_SMAGORINSKY) {
     R norm2 = S[0][0] * S[0][0] + 2 * S[1][0] * S[1][0] + 2 * S[2][0] * S[2][0] +
               S[1][1] * S[1][1] + 2 * S[2][1] * S[2][1] + S[2][2] * S[2][2];
@@ -214,6 +214,15 @@ __device__ __forceinline__ void flux_second_order(const AtmosParams<R> &P, const
     R nuc = (P.turbulence == TURB_CONST_KINEMATIC) ? P.turb_param : P.turb_param / q[0];
     nu[0] = nu[1] = nu[2] = nuc;
   }
+}
+
+template <class R>
+__device__ __forceinline__ void flux_second_order(const AtmosParams<R> &P, const R q[5],
+                                                  const R *gf, const R gradPhi[3], R Delta,
+                                                  R F2[3][5]) {
+  const R S[3][3] = {{gf[3], gf[4], gf[5]}, {gf[4], gf[6], gf[7]}, {gf[5], gf[7], gf[8]}};
+  R nu[3];
+  turbulence_nu<R>(P, q, gf, gradPhi, Delta, nu);
   R trS = S[0][0] + S[1][1] + S[2][2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -783,6 +792,116 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       A.dQ[eoffQ + (size_t)s * NP + tid] = d;
       if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// courant(local_courant, dg, m, Q, dt, simtime, direction) (SpaceDiscretization.jl:307-365):
+// kernel_min_neighbor_distance! (Grids.jl:1219-1336) + kernel_local_courant!
+// (DGModel_kernels.jl:3028-3100) + maximum, fused: one block per element, the element maximum is
+// folded into *result with an atomic max on the bit pattern (Courant numbers are >= 0).
+// kind: 0 advective, 1 nondiffusive, 2 diffusive (src/Atmos/Model/courant.jl:12-86).
+// vgeo is the caller's array in the reference layout (x1, x2, x3 = columns 12, 13, 14 of 25).
+// ---------------------------------------------------------------------------------------
+enum { COURANT_ADVECTIVE = 0, COURANT_NONDIFFUSIVE = 1, COURANT_DIFFUSIVE = 2 };
+template <class R, int NQ>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK)
+courant_kernel(const R *__restrict__ Q, const R *__restrict__ aux, const R *__restrict__ gradflux,
+               const R *__restrict__ vgeo, const AtmosParams<R> P, R dt, int kind, int direction,
+               unsigned long long *result) {
+  constexpr int NP = Dims<NQ>::NP, BLOCK = Dims<NQ>::BLOCK;
+  __shared__ R sx[3][NP];
+  __shared__ R red[BLOCK / 32];
+  const int tid = threadIdx.x, e = blockIdx.x;
+  if (tid < NP) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sx[d][tid] = vgeo[((size_t)e * 25 + 12 + d) * NP + tid];
+  }
+  __syncthreads();
+  R c = R(0);
+  if (tid < NP) {
+    const int idx[3] = {tid % NQ, (tid / NQ) % NQ, tid / (NQ * NQ)};
+    const int stride[3] = {1, NQ, NQ * NQ};
+    const bool use[3] = {direction != 2, direction != 2, direction != 1};
+    R md = sizeof(R) == 8 ? (R)1.7976931348623157e308 : (R)3.4028234e38f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (!use[d]) continue;
+#pragma unroll
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const int o = idx[d] + sgn;
+        if (o < 0 || o >= NQ) continue;
+        const int nb = tid + sgn * stride[d];
+        const R d0 = sx[0][tid] - sx[0][nb], d1 = sx[1][tid] - sx[1][nb], d2 = sx[2][tid] - sx[2][nb];
+        const R dist = sqrt_<R>(d0 * d0 + d1 * d1 + d2 * d2);
+        md = dist < md ? dist : md;
+      }
+    }
+    R q[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) q[s] = Q[((size_t)e * 5 + s) * NP + tid];
+    const size_t oa = (size_t)e * P.naux * NP + tid;
+    R k[3] = {0, 0, 0}, gP[3] = {0, 0, 0};
+    if (P.a_gradPhi >= 0) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        gP[d] = aux[oa + (size_t)(P.a_gradPhi + d) * NP];
+        k[d] = gP[d] / P.grav;
+      }
+    }
+    if (kind == COURANT_DIFFUSIVE) {
+      R gf[10];
+#pragma unroll
+      for (int s = 0; s < 10; ++s)
+        gf[s] = (s < P.ngradflux) ? gradflux[((size_t)e * P.ngradflux + s) * NP + tid] : R(0);
+      const R Delta = P.a_Delta >= 0 ? aux[oa + (size_t)P.a_Delta * NP] : R(0);
+      R nu[3];
+      turbulence_nu<R>(P, q, gf, gP, Delta, nu);
+      R nrm;
+      if (P.turbulence != TURB_SMAGORINSKY) {
+        nrm = nu[0];
+      } else {
+        const R dot = nu[0] * k[0] + nu[1] * k[1] + nu[2] * k[2];
+        if (direction == 2) nrm = dot;
+        else if (direction == 1) {
+          const R v0 = nu[0] - dot * k[0], v1 = nu[1] - dot * k[1], v2 = nu[2] - dot * k[2];
+          nrm = sqrt_<R>(v0 * v0 + v1 * v1 + v2 * v2);
+        } else nrm = sqrt_<R>(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
+      }
+      c = dt * nrm / (md * md);
+    } else {
+      R normu;
+      const R dot = q[1] * k[0] + q[2] * k[1] + q[3] * k[2];
+      if (direction == 2) normu = fabs(dot) / q[0];
+      else if (direction == 1) {
+        const R v0 = (q[1] - dot * k[0]) / q[0], v1 = (q[2] - dot * k[1]) / q[0], v2 = (q[3] - dot * k[2]) / q[0];
+        normu = sqrt_<R>(v0 * v0 + v1 * v1 + v2 * v2);
+      } else {
+        const R u0 = q[1] / q[0], u1 = q[2] / q[0], u2 = q[3] / q[0];
+        normu = sqrt_<R>(u0 * u0 + u1 * u1 + u2 * u2);
+      }
+      R ss = R(0);
+      if (kind == COURANT_NONDIFFUSIVE) {
+        const R Phi = P.a_Phi >= 0 ? aux[oa + (size_t)P.a_Phi * NP] : R(0);
+        const Thermo<R> th = thermo<R>(P, q, Phi);
+        ss = sqrt_<R>(P.gamma * P.R_d * th.T);
+      }
+      c = dt * (normu + ss) / md;
+    }
+  }
+  // block maximum (NaN-free inputs assumed; a NaN state shows up as NaN through fmax semantics elsewhere)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const R other = __shfl_xor_sync(0xffffffffu, c, o);
+    c = other > c ? other : c;
+  }
+  if ((tid & 31) == 0) red[tid >> 5] = c;
+  __syncthreads();
+  if (tid == 0) {
+    R m = red[0];
+#pragma unroll
+    for (int w = 1; w < BLOCK / 32; ++w) m = red[w] > m ? red[w] : m;
+    atomicMax(result, (unsigned long long)__double_as_longlong((double)m));
   }
 }
 

@@ -322,6 +322,20 @@ class DGModel:
         kind, mask, W, d = self._filter_args(target, filter, direction)
         _lib.check(_lib.lib().cmdg_set_step_filter(self._h, kind, mask, _ptr(W), _ptr(W), d), self._h)
 
+    # -- courant(local_courant, dg, m, Q, dt, simtime, direction) -----------------------------
+    def courant(self, local_courant, Q, Δt, direction=None):
+        """``local_courant`` in {"advective", "nondiffusive", "diffusive"} (the functions of
+        src/Atmos/Model/courant.jl); returns the rank-local maximum."""
+        kind = {"advective": _lib.COURANT_ADVECTIVE, "nondiffusive": _lib.COURANT_NONDIFFUSIVE,
+                "diffusive": _lib.COURANT_DIFFUSIVE}[local_courant]
+        d = {bl.EveryDirection: _lib.DIR_EVERY, bl.HorizontalDirection: _lib.DIR_HORIZONTAL,
+             bl.VerticalDirection: _lib.DIR_VERTICAL}[type(direction or bl.EveryDirection())]
+        out = C.c_double(0.0)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cmdg_courant(self._h, _ptr(Q.data), _ptr(self.grid.vgeo), float(Δt), kind, d,
+                                           C.byref(out), st), self._h)
+        return out.value
+
     def set_timing(self, enable=True):
         _lib.check(_lib.lib().cmdg_set_timing(self._h, int(enable)), self._h)
 

@@ -245,6 +245,20 @@ int cmdg_set_step_filter(cmdg_handle h, int32_t target, uint32_t state_mask, con
                          const void *filter_v, int32_t direction);
 
 /*
+ * Replaces `courant(local_courant, dg, m, Q, dt, simtime, direction)`,
+ * src/Numerics/DGMethods/SpaceDiscretization.jl:307-365, for the AtmosModel pointwise numbers of
+ * src/Atmos/Model/courant.jl:12-86 (kind = CMDG_COURANT_*): node distances
+ * (kernel_min_neighbor_distance!, src/Numerics/Mesh/Grids.jl:1219-1336), the pointwise number and
+ * the maximum over the rank's real elements in one kernel.  Synchronous; *result_host receives the
+ * rank-local maximum (the caller applies MPI.Allreduce(max) as the reference does).  `vgeo` is
+ * grid.vgeo (Np x 25 x nelem, device).  CMDG_COURANT_DIFFUSIVE reads the bound
+ * state_gradient_flux of the last tendency evaluation.
+ */
+enum { CMDG_COURANT_ADVECTIVE = 0, CMDG_COURANT_NONDIFFUSIVE = 1, CMDG_COURANT_DIFFUSIVE = 2 };
+int cmdg_courant(cmdg_handle h, const void *Q, const void *vgeo, double dt, int32_t kind,
+                 int32_t direction, double *result_host, cmdg_stream stream);
+
+/*
  * Halo exchange of MPIStateArray face data, src/Arrays/MPIStateArrays.jl:411-514:
  * cmdg_comm_unique_id fills a 128-byte ncclUniqueId on one rank; the caller broadcasts it
  * (MPI in Julia, torch.distributed in the Python harness); cmdg_comm_init joins the

@@ -280,6 +280,37 @@ def filter_case(direction="every", target="indices", nsteps=0, dt=0.5):
     return res
 
 
+def courant_case():
+    """courant(local_courant, dg, m, Q, dt, t, direction) for the three AtmosModel numbers and the
+    three directions, Smagorinsky on the cubed sphere (gradient flux from one tendency call)."""
+    from oracle import courant as ocourant
+    P = pkg()
+    model, gs = gcm_setup(3, 2, turbulence=("smagorinsky", 0.21))
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], "rusanov", diffusion_direction="horizontal")
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_baroclinic_wave(model, aux)
+    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
+    omsa.ghost_exchange([oQ])
+    odQ = oQ.similar()
+    odgm([odQ], [oQ], 0.0, 1, 0)
+    dg, dgrid = make_device_dg(odgm, g, "rusanov", "horizontal")
+    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    dT = P.MPIStateArray(dgrid, 5)
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    out = {}
+    dirs = {"every": P.EveryDirection, "horizontal": P.HorizontalDirection, "vertical": P.VerticalDirection}
+    for kind in ("advective", "nondiffusive", "diffusive"):
+        for dname, D in dirs.items():
+            ref = ocourant.courant(model, g, oQ.data, odgm.state_auxiliary[0].data,
+                                   odgm.state_gradient_flux[0].data, 0.5, kind, dname)
+            got = dg.courant(kind, dQ, 0.5, D())
+            out[(kind, dname)] = (got, ref)
+    dg.close()
+    return out
+
+
 def box_setup(nelem=(3, 2, 3), FT=np.float64, turbulence=("smagorinsky", 0.21), csize=1,
               periodic_z=False):
     """LES-like box (tutorials/Atmos/risingbubble.jl without tracers): flat orientation,

@@ -127,6 +127,15 @@ def test_per_step_filter_in_fused_stepper():
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+def test_courant_numbers():
+    """advective / nondiffusive / diffusive Courant numbers, every / horizontal /
+    vertical direction (node distances + pointwise number + maximum in one kernel)."""
+    out = parity.courant_case()
+    for key, (got, ref) in out.items():
+        assert ref > 0, key
+        assert abs(got - ref) <= 1e-12 * ref, (key, got, ref)
+
+
 def test_multi_gpu_halo_and_parity():
     """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU box skips it, `gpurun --gpus 2` runs it)."""
     import os
