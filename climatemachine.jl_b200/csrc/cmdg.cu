@@ -95,6 +95,9 @@ struct cmdg_handle_s {
   void *stepWh = nullptr, *stepWv = nullptr, *tmpWh = nullptr, *tmpWv = nullptr;
   int step_filter_target = -1, step_filter_dir = 0;
   unsigned step_filter_mask = 0;
+  // second-order path: diffusive flux per node (ghost part filled by the halo exchange) and its
+  // normal component at every real element's own face nodes, written by the gradient kernel
+  void *F2dev = nullptr, *FnDev = nullptr;
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
   bool grid_bound = false;
@@ -446,6 +449,9 @@ TendArgs<R> base_args(cmdg_handle h) {
   a.D = (const R *)h->Ddev;
   a.aux_out = h->d.write_aux_diagnostics ? (R *)h->aux : nullptr;
   a.pf_dist = h->pf_dist;
+  a.F2 = (const R *)h->F2dev;
+  a.Fn = (const R *)h->FnDev;
+  a.nreal = (int)h->d.nrealelem;
   return a;
 }
 
@@ -467,7 +473,7 @@ int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double 
   a.beta = (R)beta;
   a.t = (R)t;
   GradArgs<R> ga{(const R *)Q, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
-                 (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev};
+                 (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev};
   int rc;
   if (!par) {
     if (h->visc) {
@@ -484,12 +490,12 @@ int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double 
     if ((rc = exchange_end_t<R>(h, Q, h->d.nstate, st))) return rc;
     ga.elems = h->exterior;
     if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
-    if ((rc = exchange_begin_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
   }
   a.elems = h->interior;
   if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
   if (h->visc) {
-    if ((rc = exchange_end_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, h->F2dev, 12, st))) return rc;
   } else {
     if ((rc = exchange_end_t<R>(h, Q, h->d.nstate, st))) return rc;
   }
@@ -588,7 +594,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       // aux diagnostics are refreshed by the last stage only (they are read after steps)
       if (s != nstage - 1) a.aux_out = nullptr;
       GradArgs<R> ga{cur, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
-                     (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev};
+                     (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev};
       int rc;
       if (!par) {
         if (h->visc && (rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
@@ -598,10 +604,10 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
         if (h->visc) {
           ga.elems = h->exterior;
           if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
-          if ((rc = exchange_begin_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+          if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
           ga.elems = h->interior;
           if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
-          if ((rc = exchange_end_t<R>(h, h->gradflux, h->d.ngradflux, st))) return rc;
+          if ((rc = exchange_end_t<R>(h, h->F2dev, 12, st))) return rc;
         }
         // a per-step filter changes the new state after the last stage: its halo goes out after
         // the filter instead of overlapping the interior kernel
@@ -891,7 +897,7 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev};
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -993,6 +999,15 @@ int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
     return fail(h, CMDG_ERR_INVALID, "state_gradient_flux is required unless skip_zero_viscosity applies");
   h->aux = aux;
   h->gradflux = gradflux;
+  if (h->visc && !h->is_hb && !h->F2dev) {
+    // private outputs of the gradient kernel (zeroed: ghost entries are read before the first exchange
+    // only on single-rank runs that have no ghosts)
+    const size_t f2 = (size_t)h->d.nelem * 12 * h->Np * h->fb, fn = (size_t)h->d.nrealelem * 6 * h->Nfp * 4 * h->fb;
+    CU(cudaMalloc(&h->F2dev, f2 + 16));
+    CU(cudaMalloc(&h->FnDev, fn + 16));
+    CU(cudaMemset(h->F2dev, 0, f2));
+    CU(cudaMemset(h->FnDev, 0, fn));
+  }
   return CMDG_OK;
 }
 

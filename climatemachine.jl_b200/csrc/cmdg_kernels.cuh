@@ -73,6 +73,10 @@ struct TendArgs {
   R rkb_dt;            // Qout = Q + rkb_dt * dQ
   R t;
   int pf_dist;         // L2 prefetch distance in launch-list entries (0 = off)
+  // second-order path: diffusive flux evaluated once per node by the gradient kernel
+  const R *F2;         // [nelem][12][Np]   F2[d][s], s = 1..4, at column 4*d + s-1 (ghosts by exchange)
+  const R *Fn;         // [nreal][6*Nfp][4] n . F2 at the element's own face nodes
+  int nreal;
 };
 
 // conn.y layout: bits 0-2 neighbour face (0..5), bit 3 flip of first face index,
@@ -348,8 +352,7 @@ struct TendSmem {
   R P[NP], Rinv[NP];                       // own pressure, 1/rho
   R Phi[AUX ? NP : 1], Pref[AUX ? NP : 1]; // own geopotential, reference pressure
   R Ap[2][AUX ? NFN : 1];                  // neighbour geopotential, reference pressure
-  R GF[VISC ? 10 : 1][VISC ? NP : 1];      // own gradient flux
-  R GFp[VISC ? 10 : 1][VISC ? NFN : 1];    // neighbour gradient flux
+  alignas(16) R Fnp[VISC ? NFN : 1][4];    // neighbour's n+ . F2+ at my face items (16-byte cp.async)
 };
 
 #ifndef CMDG_TEND_MINBLOCKS
@@ -409,7 +412,6 @@ __global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (VISC ? 4 : CMDG_T
 dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
-  constexpr int NGF = 10;  // max gradient-flux columns
   constexpr int NWARP = BLOCK / 32;
   constexpr int FSTRIDE = (NWARP - 1) * 32;              // face threads per block
   constexpr int NITEM = (NFN + FSTRIDE - 1) / FSTRIDE;   // face items per face thread
@@ -458,8 +460,10 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       if (lo >= 0 && hi > lo)
         prefetch_l2_bulk(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R));
     }
-    if (VISC)
-      prefetch_l2_bulk(A.gradflux + (size_t)en * P.ngradflux * NP, (size_t)P.ngradflux * NP * sizeof(R));
+    if (VISC) {
+      prefetch_l2_bulk(A.F2 + (size_t)en * 12 * NP, (size_t)12 * NP * sizeof(R));
+      if (en < A.nreal) prefetch_l2_bulk(A.Fn + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
+    }
     asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
   }
 
@@ -468,9 +472,9 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   R dQold[5] = {0, 0, 0, 0, 0};
   R q[5] = {1, 0, 0, 0, 0};
   R g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  R Phi = 0, pref = 0, rref = 0, Delta = 0;
+  R Phi = 0, pref = 0, rref = 0;
   R gPhi[3] = {0, 0, 0};
-  R gf[NGF];
+  R f2[12];
   if (tid < NP) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = Qg[eoffQ + (size_t)s * NP + tid];
@@ -479,17 +483,16 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       if (P.a_ref_p >= 0) pref = auxg[eoffA + (size_t)P.a_ref_p * NP + tid];
       if ((P.sources & SRC_GRAVITY) && P.subtract_off)
         rref = auxg[eoffA + (size_t)P.a_ref_rho * NP + tid];
-      if (P.a_gradPhi >= 0 && (VISC || (P.sources & SRC_GRAVITY))) {
+      if (P.a_gradPhi >= 0 && (P.sources & SRC_GRAVITY)) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) gPhi[d] = auxg[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
       }
     }
     if (VISC) {
-      const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+      // diffusive flux of my node, evaluated by the gradient kernel (12 coalesced loads)
+      const size_t eoffF = (size_t)e * 12 * NP + tid;
 #pragma unroll
-      for (int s = 0; s < NGF; ++s)
-        gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
-      if (AUX && P.a_Delta >= 0) Delta = auxg[eoffA + (size_t)P.a_Delta * NP + tid];
+      for (int c = 0; c < 12; ++c) f2[c] = A.F2[eoffF + (size_t)c * NP];
     }
     load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
   }
@@ -513,11 +516,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
         if (P.a_ref_p >= 0)
           cp_async<sizeof(R)>(&S.Ap[1][AUX ? it : 0], auxg + offa + (size_t)P.a_ref_p * NP);
       }
-      if (VISC) {
-        const size_t offg = (size_t)cn[r].x * P.ngradflux * NP + vp;
-        for (int s = 0; s < P.ngradflux; ++s)
-          cp_async<sizeof(R)>(&S.GFp[VISC ? s : 0][VISC ? it : 0],
-                              A.gradflux + offg + (size_t)s * NP);
+      if (VISC && cn[r].x < A.nreal) {
+        // the neighbour's own normal diffusive flux at the matching face node (32 contiguous bytes)
+        const R *fnp = A.Fn + ((size_t)cn[r].x * NFN + (cn[r].y & 7) * NFP + a + NQ * b) * 4;
+        cp_async<2 * sizeof(R)>(&S.Fnp[VISC ? it : 0][0], fnp);
+        cp_async<2 * sizeof(R)>(&S.Fnp[VISC ? it : 0][2], fnp + 2);
       }
     }
   }
@@ -553,13 +556,9 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     }
     if (VISC) {
 #pragma unroll
-      for (int s = 0; s < NGF; ++s) S.GF[VISC ? s : 0][VISC ? tid : 0] = gf[s];
-      R F2[3][5];
-      flux_second_order<R>(P, q, gf, gPhi, Delta, F2);
-#pragma unroll
       for (int d = 0; d < 3; ++d)
 #pragma unroll
-        for (int s = 0; s < 5; ++s) F[d][s] += F2[d][s];
+        for (int s = 1; s < 5; ++s) F[d][s] += f2[4 * d + s - 1];
     }
 #pragma unroll
     for (int m = 0; m < 3; ++m)
@@ -585,7 +584,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       R x[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) x[d] = auxg[eoffA + (size_t)d * NP + tid];
-      if (!(VISC || (P.sources & SRC_GRAVITY))) {
+      if (!(P.sources & SRC_GRAVITY)) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) gPhi[d] = auxg[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
       }
@@ -674,20 +673,14 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
     R n[3], sMvMI;
     load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
-    // Smagorinsky needs grad Phi and Delta of both sides at the face node: issue these (L2) loads
-    // now so that their latency hides behind the first-order flux
-    R gPm[3] = {0, 0, 0}, gPp[3] = {0, 0, 0}, Dm = 0, Dp = 0;
-    if (VISC && bctag == 0 && P.turbulence == TURB_SMAGORINSKY) {
-      const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
-      const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
-      const size_t om = eoffA + vm, op = (size_t)c.x * P.naux * NP + vp;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        gPm[d] = auxg[om + (size_t)(P.a_gradPhi + d) * NP];
-        gPp[d] = auxg[op + (size_t)(P.a_gradPhi + d) * NP];
-      }
-      Dm = auxg[om + (size_t)P.a_Delta * NP];
-      Dp = auxg[op + (size_t)P.a_Delta * NP];
+    // second-order path: my own normal diffusive flux n . F2- (gradient kernel), loaded early
+    typename Vec2<R>::type fnm0, fnm1;
+    fnm0.x = fnm0.y = fnm1.x = fnm1.y = R(0);
+    if (VISC && bctag == 0) {
+      const typename Vec2<R>::type *pf =
+          reinterpret_cast<const typename Vec2<R>::type *>(A.Fn + ((size_t)e * NFN + it) * 4);
+      fnm0 = pf[0];
+      fnm1 = pf[1];
     }
     R qm[5], qp[5];
 #pragma unroll
@@ -742,21 +735,27 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 5; ++s) fl[s] -= diss[s];
     }
     if (VISC && bctag == 0) {
-      // CentralNumericalFluxSecondOrder (NumericalFluxes.jl:668-715); wall faces carry no
-      // diffusive flux for FreeSlip/NoSlip + Insulating (bc_momentum.jl:44-49, bc_energy.jl:12-17)
-      R gfm[NGF], gfp[NGF];
+      // CentralNumericalFluxSecondOrder (NumericalFluxes.jl:668-715): n . (F2- + F2+) / 2 with each
+      // side's flux evaluated once per node by the gradient kernel; wall faces carry no diffusive
+      // flux for FreeSlip/NoSlip + Insulating (bc_momentum.jl:44-49, bc_energy.jl:12-17)
+      R fnp[4];
+      if (c.x < A.nreal) {
+        // the neighbour stored n+ . F2+ with its own (opposite) normal
 #pragma unroll
-      for (int s = 0; s < NGF; ++s) {
-        gfm[s] = S.GF[VISC ? s : 0][VISC ? vm : 0];
-        gfp[s] = (s < P.ngradflux) ? S.GFp[VISC ? s : 0][VISC ? it : 0] : R(0);
+        for (int s = 0; s < 4; ++s) fnp[s] = -S.Fnp[VISC ? it : 0][s];
+      } else {
+        // ghost neighbour: its F2 arrived by the halo exchange, contract with my normal
+        const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
+        const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
+        const R *pg = A.F2 + (size_t)c.x * 12 * NP + vp;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          fnp[s] = n[0] * pg[(size_t)s * NP] + n[1] * pg[(size_t)(4 + s) * NP] + n[2] * pg[(size_t)(8 + s) * NP];
       }
-      R F2m[3][5], F2p[3][5];
-      flux_second_order<R>(P, qm, gfm, gPm, Dm, F2m);
-      flux_second_order<R>(P, qp, gfp, gPp, Dp, F2p);
-#pragma unroll
-      for (int s = 0; s < 5; ++s)
-        fl[s] += R(0.5) * ((F2m[0][s] + F2p[0][s]) * n[0] + (F2m[1][s] + F2p[1][s]) * n[1] +
-                           (F2m[2][s] + F2p[2][s]) * n[2]);
+      fl[1] += R(0.5) * (fnm0.x + fnp[0]);
+      fl[2] += R(0.5) * (fnm0.y + fnp[1]);
+      fl[3] += R(0.5) * (fnm1.x + fnp[2]);
+      fl[4] += R(0.5) * (fnm1.y + fnp[3]);
     }
     // stash vMI*sM*F* in place of the neighbour trace (same thread wrote/reads this slot)
 #pragma unroll
@@ -1008,6 +1007,10 @@ struct GradArgs {
   const int2 *conn;
   const int *elems;
   const R *D;
+  // outputs for the tendency kernel (private): diffusive flux per node and its normal component at
+  // the element's own face nodes (NULL = not wanted)
+  R *F2;   // [nelem][12][Np]
+  R *Fn;   // [nreal][6*Nfp][4]
 };
 
 template <class R>
@@ -1183,6 +1186,43 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][5 * NFP + i + NQ * j];
     const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
     for (int s = 0; s < P.ngradflux; ++s) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
+  }
+  if (!A.F2) return;
+  // ---- second-order flux F2(Q, GF, aux) of this node, once (flux_second_order!, kernels.jl:84-105):
+  // the tendency kernel then needs no closure evaluation, neither in the volume nor on faces.
+  // F2 goes to global memory (volume term, ghost exchange) and, through shared memory, into
+  // n . F2 at the element's 6 * Nfp own face nodes.
+  __syncthreads();                       // sFace has been consumed
+  R(*sF2)[NP] = reinterpret_cast<R(*)[NP]>(&sFace[0][0]);   // 12 * Np <= 10 * 6 * Nfp doubles
+  static_assert(12 * NP <= 10 * NFN, "F2 staging reuses the face buffer");
+  if (tid < NP) {
+    R Delta = R(0);
+    if (AUX && P.a_Delta >= 0) Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
+    R F2[3][5];
+    flux_second_order<R>(P, q, gfv, gPhi, Delta, F2);
+    const size_t eoffF = (size_t)e * 12 * NP + tid;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int c = 1; c < 5; ++c) {
+        A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
+        sF2[4 * d + c - 1][tid] = F2[d][c];
+      }
+  }
+  __syncthreads();
+  for (int it = tid; it < NFN; it += BLOCK) {
+    const int f = it / NFP, fn = it - f * NFP;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    R n[3], sMvMI;
+    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
+    typename Vec2<R>::type o0, o1;
+    o0.x = n[0] * sF2[0][vm] + n[1] * sF2[4][vm] + n[2] * sF2[8][vm];
+    o0.y = n[0] * sF2[1][vm] + n[1] * sF2[5][vm] + n[2] * sF2[9][vm];
+    o1.x = n[0] * sF2[2][vm] + n[1] * sF2[6][vm] + n[2] * sF2[10][vm];
+    o1.y = n[0] * sF2[3][vm] + n[1] * sF2[7][vm] + n[2] * sF2[11][vm];
+    typename Vec2<R>::type *po = reinterpret_cast<typename Vec2<R>::type *>(A.Fn + ((size_t)e * NFN + it) * 4);
+    po[0] = o0;
+    po[1] = o1;
   }
 }
 
