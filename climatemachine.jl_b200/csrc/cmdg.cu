@@ -273,6 +273,7 @@ int launch_tendency(cmdg_handle h, const TendArgs<R> &a, int64_t n, cudaStream_t
 template <class R>
 int launch_gradient(cmdg_handle h, const GradArgs<R> &a, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
+  if (int rc = ensure_const_D<R>(h, st)) return rc;
   const AtmosParams<R> P = make_params<R>(h);
   if (h->aux_model)
     dg_gradient_kernel<R, 5, true><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);

@@ -408,7 +408,10 @@ __device__ __forceinline__ void extended_sources(const AtmosParams<R> &P, const 
 }
 
 template <class R, int NQ, int NF1, bool AUX, bool VISC, bool SRCX>
-__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (VISC ? 4 : CMDG_TEND_MINBLOCKS) : 1))
+#ifndef CMDG_VISC_MINBLOCKS
+#define CMDG_VISC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (VISC ? CMDG_VISC_MINBLOCKS : CMDG_TEND_MINBLOCKS) : 1))
 dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
@@ -1021,7 +1024,11 @@ __device__ __forceinline__ void gradient_argument(const AtmosParams<R> &P, const
   G[1] = th.rinv * q[2];
   G[2] = th.rinv * q[3];
   G[3] = q[4] * th.rinv + P.R_d * th.T;
-  G[4] = th.T / pow_<R>(th.p / P.MSLP, P.kappa);  // aux.moisture.theta_v, refreshed from Q
+  // aux.moisture.theta_v, refreshed from Q; only the Smagorinsky closure differentiates it.
+  // (p / MSLP)^kappa as exp(kappa log(.)): half the instructions of pow, same value to 1e-16
+  G[4] = (P.turbulence == TURB_SMAGORINSKY)
+             ? th.T / exp_<R>(P.kappa * log_<R>(th.p / P.MSLP))
+             : R(0);
 }
 
 // gf = linear map of the gradient  dG[d][g]  (TurbulenceClosures.jl:351-362,456-470)
@@ -1042,8 +1049,11 @@ __device__ __forceinline__ void gradient_flux(const AtmosParams<R> &P, const R d
               : R(0);
 }
 
+#ifndef CMDG_GRAD_MINBLOCKS
+#define CMDG_GRAD_MINBLOCKS 5
+#endif
 template <class R, int NQ, bool AUX>
-__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? CMDG_GRAD_MINBLOCKS : 1))
 dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
@@ -1051,15 +1061,37 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   __shared__ R sQ[5][NP];
   __shared__ R sPhi[AUX ? NP : 1];
   __shared__ R sFace[10][NFN];
-  __shared__ R sD[NQ * NQ];
-  __shared__ int2 sConn[6];
+  __shared__ R sQp[6][NFN];      // neighbour traces (Q+, Phi+), gathered asynchronously
+  constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const size_t eoffQ = (size_t)e * 5 * NP;
   const size_t eoffA = (size_t)e * P.naux * NP;
-  if (tid < 6) sConn[tid] = A.conn[(size_t)e * 6 + tid];
-  if (tid < NQ * NQ) sD[tid] = A.D[tid];
   const int nfaces = P.horizontal_diffusion ? 4 : 6;
+  // face descriptors of my items, then cp.async gathers of the neighbour state: their latency
+  // overlaps the node phase (the same thread consumes what it gathered: no barrier needed)
+  int2 cn[NITEM];
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    cn[r] = (it < nfaces * NFP) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 16);
+  }
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    if (it < nfaces * NFP && ((cn[r].y >> 4) & 15) == 0) {
+      const int fn = it % NFP;
+      int a = fn % NQ;
+      const int b = fn / NQ;
+      if (cn[r].y & 8) a = NQ - 1 - a;
+      const int vp = face_to_vol<NQ>(cn[r].y & 7, a, b);
+      const size_t offp = (size_t)cn[r].x * 5 * NP + vp;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&sQp[s][it], A.Q + offp + (size_t)s * NP);
+      if (AUX && P.a_Phi >= 0)
+        cp_async<sizeof(R)>(&sQp[5][it], A.aux + (size_t)cn[r].x * P.naux * NP + (size_t)P.a_Phi * NP + vp);
+    }
+  }
 
   R q[5] = {1, 0, 0, 0, 0}, G[5], Phi = 0, gPhi[3] = {0, 0, 0};
   if (tid < NP) {
@@ -1081,9 +1113,13 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   __syncthreads();
 
   // faces: vMI sM gf(n (x) (G* - G-)),  G* = (G+ + G-)/2 or g(boundary_state(Q-))
-  for (int it = tid; it < nfaces * NFP; it += BLOCK) {
+  cp_async_wait_all();
+#pragma unroll
+  for (int r = 0; r < NITEM; ++r) {
+    const int it = tid + r * BLOCK;
+    if (it >= nfaces * NFP) break;
     const int f = it / NFP, fn = it - f * NFP;
-    const int2 c = sConn[f];
+    const int2 c = cn[r];
     const int bctag = (c.y >> 4) & 15;
     const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
     R n[3], sMvMI;
@@ -1101,14 +1137,10 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int d = 0; d < 3; ++d) gPm[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + vm];
     }
     if (bctag == 0) {
-      int a = fn % NQ, b = fn / NQ;
-      if (c.y & 8) a = NQ - 1 - a;
-      const int vp = face_to_vol<NQ>(c.y & 7, a, b);
-      const size_t offp = (size_t)c.x * 5 * NP + vp;
 #pragma unroll
-      for (int s = 0; s < 5; ++s) qp[s] = A.Q[offp + (size_t)s * NP];
+      for (int s = 0; s < 5; ++s) qp[s] = sQp[s][it];
       R Phip = 0;
-      if (AUX && P.a_Phi >= 0) Phip = A.aux[(size_t)c.x * P.naux * NP + (size_t)P.a_Phi * NP + vp];
+      if (AUX && P.a_Phi >= 0) Phip = sQp[5][it];
       gradient_argument<R>(P, qp, Phip, Gs);
 #pragma unroll
       for (int s = 0; s < 5; ++s) Gs[s] = R(0.5) * (Gs[s] + Gm[s]) - Gm[s];
@@ -1151,7 +1183,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
     R G1[5] = {0, 0, 0, 0, 0}, G2[5] = {0, 0, 0, 0, 0}, G3[5] = {0, 0, 0, 0, 0};
 #pragma unroll
     for (int n = 0; n < NQ; ++n) {
-      const R d1 = sD[i * NQ + n], d2 = sD[j * NQ + n], d3 = sD[k * NQ + n];
+      const R d1 = const_D<R>(i * NQ + n), d2 = const_D<R>(j * NQ + n), d3 = const_D<R>(k * NQ + n);
       const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
 #pragma unroll
       for (int s = 0; s < 5; ++s) {

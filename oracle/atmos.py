@@ -97,7 +97,7 @@ class DryAtmosModel:
 
     def __init__(self, FT=np.float64, orientation="none", ref_state=None,
                  turbulence=("constant_dynamic", 0.0, False), sources=(),
-                 bcs=(), params=None):
+                 bcs=(), params=None, hyperdiffusion=None):
         self.FT = np.dtype(FT).type
         self.ps = params or Params(FT)
         self.orientation = orientation            # none | flat | spherical
@@ -123,18 +123,36 @@ class DryAtmosModel:
         if turbulence[0] == "smagorinsky":
             self.a_Δ = c
             c += 1
+        # DryBiharmonic hyperdiffusion (TurbulenceClosures.jl:793-848): ("dry_biharmonic", tau)
+        self.hyperdiffusion = hyperdiffusion
+        self.a_Δh = None
+        if hyperdiffusion is not None:
+            assert hyperdiffusion[0] == "dry_biharmonic"
+            self.a_Δh = c
+            c += 1
         self.a_θv = c
         self.a_T = c + 1
         self.A = c + 2
         # gradient / gradient-flux layout
-        self.G = 5 if turbulence[0] == "smagorinsky" else 4
-        self.GF = 10 if turbulence[0] == "smagorinsky" else 9
+        self.smag = turbulence[0] == "smagorinsky"
+        self.G = 5 if self.smag else 4
+        self.GF = 10 if self.smag else 9
+        # Gradient vars: u, h_tot, [theta_v], [hyperdiffusion: u_h (3), h_tot]; the last four are the
+        # GradientLaplacian variables (hypervisc_indexmap), Hyperdiffusive = nu grad^3 u_h (3x3
+        # column major), nu grad^3 h_tot (3)
+        self.hyper_G = None
+        self.ngradlap = self.nhyper = 0
+        if hyperdiffusion is not None:
+            self.hyper_G = self.G
+            self.G += 4
+            self.ngradlap, self.nhyper = 4, 12
         self.subtract_off = bool(ref_state is not None and ref_state.get("subtract_off", True))
 
     # ------------------------------------------------------------------
     def viscous(self):
         """True when second-order fluxes can be non-zero."""
-        return not (self.turbulence[0].startswith("constant") and self.turbulence[1] == 0)
+        return self.hyperdiffusion is not None or \
+            not (self.turbulence[0].startswith("constant") and self.turbulence[1] == 0)
 
     def Φ(self, aux):
         if self.a_Φ is None:
@@ -262,9 +280,40 @@ class DryAtmosModel:
         T, _ = self.thermo(Q, aux)
         e_tot = Q[4] * (1 / Q[0])
         G[3] = e_tot + self.ps.R_d * T
-        if self.G == 5:
+        if self.smag:
             G[4] = aux[self.a_θv]
+        if self.hyper_G is not None:
+            # compute_gradient_argument!(::DryBiharmonic, ...): u_h = (I - k k') u, h_tot
+            k = aux[self.a_gradΦ] / self.ps.grav
+            u = G[0:3]
+            ku = k[0] * u[0] + k[1] * u[1] + k[2] * u[2]
+            G[self.hyper_G:self.hyper_G + 3] = u - k * ku
+            G[self.hyper_G + 3] = G[3]
         return G
+
+    def transform_post_gradient_laplacian(self, gradlap, Q, aux):
+        """``transform_post_gradient_laplacian!(::DryBiharmonic, ...)``: gradlap[d, g] ->
+        hyperdiffusive (12, ...): nu4 grad(lap u_h) at d + 3 c, nu4 grad(lap h_tot) at 9 + d."""
+        τ = self.FT(self.hyperdiffusion[1])
+        ν4 = (aux[self.a_Δh] / 2) ** 4 / 2 / τ
+        H = np.zeros((12,) + Q.shape[1:], dtype=Q.dtype)
+        for c in range(3):
+            for d in range(3):
+                H[d + 3 * c] = ν4 * gradlap[d, c]
+        for d in range(3):
+            H[9 + d] = ν4 * gradlap[d, 3]
+        return H
+
+    def flux_hyperdiffusive(self, Q, H):
+        """HyperdiffViscousFlux / HyperdiffEnthalpyFlux (tendencies_momentum.jl:51-54,
+        tendencies_energy.jl:40-48): F[d, 1 + c] = rho H[d, c]; F[d, 4] = H[d, :] . rhou + H_h[d] rho."""
+        F = np.zeros((3, 5) + Q.shape[1:], dtype=Q.dtype)
+        ρ, ρu = Q[0], Q[1:4]
+        for d in range(3):
+            for c in range(3):
+                F[d, 1 + c] = ρ * H[d + 3 * c]
+            F[d, 4] = (H[d] * ρu[0] + H[d + 3] * ρu[1] + H[d + 6] * ρu[2]) + H[9 + d] * ρ
+        return F
 
     def gradient_flux(self, gradG, Q, aux):
         """gradG[d, g, ...] -> GF (linear in gradG)."""

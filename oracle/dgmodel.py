@@ -10,6 +10,12 @@ Restates, with the reference's launch schedule and accumulation order:
 * ``launch_volume_gradients!`` / ``volume_gradients!``   <- ``SpaceDiscretization.jl:502-585``, ``DGModel_kernels.jl:934-1328``
 * ``dgsem_interface_gradients!``                         <- ``DGModel_kernels.jl:1365-1651``
 * nodal auxiliary update                                 <- ``DGModel_kernels.jl:1769-1825``, ``SpaceDiscretization.jl:157-212``
+* hyperdiffusion passes (DryBiharmonic, horizontal diffusion direction): gradients stored by the
+  gradient kernels (``DGModel_kernels.jl:1081-1098,1618-1628``), ``volume_divergence_of_gradients!``
+  (``:2132-2228``), ``interface_divergence_of_gradients!`` (``:2359-2490``),
+  ``volume_gradients_of_laplacians!`` (``:2521-2680``), ``interface_gradients_of_laplacians!``
+  (``:2860-3026``), ``CentralNumericalFluxDivergence`` / ``CentralNumericalFluxHigherOrder``
+  (``NumericalFluxes.jl:716-835``), schedule ``DGModel.jl:226-310``
 * numerical fluxes Rusanov / Central / Roe, boundary-flux plumbing,
   central gradient and second-order fluxes               <- ``NumericalFluxes.jl:65-123,163-340,668-715,872-918``
 * auxiliary initialisation (coord, Phi, grad Phi by the element-local strong
@@ -47,6 +53,13 @@ class DGModel:
         bl = balance_law
         self.state_auxiliary = [MPIStateArray.from_grid(g, bl.A) for g in self.grids]
         self.state_gradient_flux = [MPIStateArray.from_grid(g, bl.GF) for g in self.grids]
+        self.nhyper = getattr(bl, "nhyper", 0)
+        if self.nhyper:
+            # states_higher_order (create_states.jl:20-27): max(3 * ngradlap, nhyper) and ngradlap columns
+            assert diffusion_direction == "horizontal", \
+                "hyperdiffusion: only HorizontalDirection (the reference's 3-D EveryDirection kernel is broken)"
+            self.Qhypervisc_grad = [MPIStateArray.from_grid(g, max(3 * bl.ngradlap, bl.nhyper)) for g in self.grids]
+            self.Qhypervisc_div = [MPIStateArray.from_grid(g, bl.ngradlap) for g in self.grids]
         if init_aux:
             self.init_state_auxiliary()
 
@@ -145,6 +158,8 @@ class DGModel:
                        - vg[:, 3] * (vg[:, 1] * vg[:, 8] - vg[:, 7] * vg[:, 2])
                        + vg[:, 6] * (vg[:, 1] * vg[:, 5] - vg[:, 4] * vg[:, 2]))
                 a[bl.a_Δ][:nr] = 2 / (np.cbrt(det) * max(1, *g.N))
+            if getattr(bl, "a_Δh", None) is not None:
+                a[bl.a_Δh][:nr] = lengthscale_horizontal(g)
         ghost_exchange(self.state_auxiliary)
 
     def reference_pressure_gradient(self):
@@ -241,6 +256,9 @@ class DGModel:
             F = bl.flux_first_order(qs, a)
             if bl.GF > 0 and not self._skip2():
                 F = F + bl.flux_second_order(qs, _sv(gf.data[:nr]), a)
+                if self.nhyper:
+                    hg = self.Qhypervisc_grad[self.grids.index(g)]
+                    F = F + bl.flux_hyperdiffusive(qs, _sv(hg.data[:nr]))
             src = bl.source(qs, a)
             self._volume_weak_divergence(g, F, src)
             d = _sv(dq.data[:nr])
@@ -318,6 +336,10 @@ class DGModel:
                     Qp2 = np.moveaxis(q.data[ep, :, vp], -1, 0)
                     ap2 = np.moveaxis(aux.data[ep, :, vp], -1, 0)
                     F2 = F2 + bl.flux_second_order(Qp2, gp, ap2)
+                    if self.nhyper:
+                        hg = self.Qhypervisc_grad[self.grids.index(g)]
+                        F2 = F2 + bl.flux_hyperdiffusive(Qm, np.moveaxis(hg.data[em, :, vm], -1, 0))
+                        F2 = F2 + bl.flux_hyperdiffusive(Qp2, np.moveaxis(hg.data[ep, :, vp], -1, 0))
                     fl2 = F2[0] * (n[0] / 2) + F2[1] * (n[1] / 2) + F2[2] * (n[2] / 2)
                     # AtmosBC FreeSlip/NoSlip + Insulating: no diffusive boundary flux; models with
                     # flux-based BCs (normal_boundary_flux_second_order!, NumericalFluxes.jl:872-967)
@@ -363,6 +385,11 @@ class DGModel:
             if self.diffusion_direction == "every":
                 gradV = np.stack([vg[:, G._xi3x1 + 3 * d] * G3 for d in range(3)])
                 gfs[...] = gfs + bl.gradient_flux(gradV, qs, a)
+            if self.nhyper:
+                hg = _sv(self.Qhypervisc_grad[self.grids.index(g)].data[:nr])
+                for s_ in range(bl.ngradlap):
+                    for d in range(3):
+                        hg[3 * s_ + d] = gradH[d, bl.hyper_G + s_]
 
     def interface_gradients(self, Q, t, which):
         bl = self.bl
@@ -394,6 +421,99 @@ class DGModel:
                 for s in range(bl.GF):
                     cur = gf.data[em, s, vm]
                     gf.data[em, s, vm] = cur + vMI * sM * (gfstar[s] - gfm[s])
+                if self.nhyper:
+                    hg = self.Qhypervisc_grad[self.grids.index(g)]
+                    for s_ in range(bl.ngradlap):
+                        j = bl.hyper_G + s_
+                        for d in range(3):
+                            cur = hg.data[em, 3 * s_ + d, vm]
+                            hg.data[em, 3 * s_ + d, vm] = cur + vMI * sM * (nGstar[d, j] - nGm[d, j])
+
+    # ------------------------------------------------------------------
+    # hyperdiffusion passes (HorizontalDirection)
+    # ------------------------------------------------------------------
+    def volume_divergence_of_gradients(self):
+        """Qhypervisc_div[s] = -MI D^T (M xi_x . grad G_s), xi1 and xi2 only."""
+        bl = self.bl
+        for g, hg, hd in zip(self.grids, self.Qhypervisc_grad, self.Qhypervisc_div):
+            nr, Nq = g.nreal, g.Nq
+            vg = g.vgeo[:nr]
+            M, MI = vg[:, G._M], vg[:, G._MI]
+            gr = _sv(hg.data[:nr])
+            shp = (nr, Nq[2], Nq[1], Nq[0])
+            MIr = MI.reshape(shp)
+            D1, D2, _ = g.D
+            for s_ in range(bl.ngradlap):
+                G1, G2, G3 = gr[3 * s_], gr[3 * s_ + 1], gr[3 * s_ + 2]
+                s1 = (M * (vg[:, G._xi1x1] * G1 + vg[:, G._xi1x2] * G2 + vg[:, G._xi1x3] * G3)).reshape(shp)
+                s2 = (M * (vg[:, G._xi2x1] * G1 + vg[:, G._xi2x2] * G2 + vg[:, G._xi2x3] * G3)).reshape(shp)
+                div = np.zeros(shp, dtype=hg.data.dtype)
+                for n in range(Nq[0]):
+                    div = div - MIr * D1[n, :] * s1[..., n:n + 1]
+                    div = div - MIr * D2[n, :][:, None] * s2[:, :, n:n + 1, :]
+                hd.data[:nr, s_] = div.reshape(nr, g.Np)
+
+    def interface_divergence_of_gradients(self, which):
+        """+= vMI sM (grad+ + grad-)' n / 2; walls: grad+ = grad- (boundary_state! is a no-op)."""
+        bl = self.bl
+        for g, hg, hd in zip(self.grids, self.Qhypervisc_grad, self.Qhypervisc_div):
+            elems = (g.interiorelems if which == "interior" else g.exteriorelems) - 1
+            if len(elems) == 0:
+                continue
+            for f in range(4):
+                em, vm, ep, vp, bnd = self._face_data(g, elems, f, hg.data)
+                n = np.stack([g.sgeo[elems, f, :, c] for c in range(3)])
+                sM, vMI = g.sgeo[elems, f, :, G._sM], g.sgeo[elems, f, :, G._vMI]
+                gm = np.moveaxis(hg.data[em, :, vm], -1, 0)
+                gp = np.moveaxis(hg.data[ep, :, vp], -1, 0)
+                for s_ in range(bl.ngradlap):
+                    ldiv = 0
+                    for d in range(3):
+                        ldiv = ldiv + (gp[3 * s_ + d] + gm[3 * s_ + d]) * (n[d] / 2)
+                    cur = hd.data[em, s_, vm]
+                    hd.data[em, s_, vm] = cur + vMI * sM * ldiv
+
+    def volume_gradients_of_laplacians(self, Q):
+        """Qhypervisc_grad = transform(xi_x D lap), xi1 and xi2 only (strong form)."""
+        bl = self.bl
+        for g, q, aux, hg, hd in zip(self.grids, Q, self.state_auxiliary, self.Qhypervisc_grad,
+                                     self.Qhypervisc_div):
+            nr, Nq = g.nreal, g.Nq
+            vg = g.vgeo[:nr]
+            shp = (bl.ngradlap, nr, Nq[2], Nq[1], Nq[0])
+            lap = _sv(hd.data[:nr]).reshape(shp)
+            D1, D2, _ = g.D
+            L1 = np.zeros(shp, dtype=hd.data.dtype)
+            L2 = np.zeros(shp, dtype=hd.data.dtype)
+            for n in range(Nq[0]):
+                L1 = L1 + D1[:, n] * lap[..., n:n + 1]
+                L2 = L2 + D2[:, n][:, None] * lap[:, :, :, n:n + 1, :]
+            L1, L2 = L1.reshape(bl.ngradlap, nr, g.Np), L2.reshape(bl.ngradlap, nr, g.Np)
+            gl = np.stack([vg[:, G._xi1x1 + 3 * d] * L1 + vg[:, G._xi2x1 + 3 * d] * L2 for d in range(3)])
+            H = bl.transform_post_gradient_laplacian(gl, _sv(q.data[:nr]), _sv(aux.data[:nr]))
+            _sv(hg.data[:nr])[...] = H
+
+    def interface_gradients_of_laplacians(self, Q, which):
+        """+= vMI sM transform(n (lap+ - lap-) / 2) with the minus-side state; walls: lap+ = lap-."""
+        bl = self.bl
+        for g, q, aux, hg, hd in zip(self.grids, Q, self.state_auxiliary, self.Qhypervisc_grad,
+                                     self.Qhypervisc_div):
+            elems = (g.interiorelems if which == "interior" else g.exteriorelems) - 1
+            if len(elems) == 0:
+                continue
+            for f in range(4):
+                em, vm, ep, vp, bnd = self._face_data(g, elems, f, hd.data)
+                n = np.stack([g.sgeo[elems, f, :, c] for c in range(3)])
+                sM, vMI = g.sgeo[elems, f, :, G._sM], g.sgeo[elems, f, :, G._vMI]
+                lm = np.moveaxis(hd.data[em, :, vm], -1, 0)
+                lp = np.moveaxis(hd.data[ep, :, vp], -1, 0)
+                Qm = np.moveaxis(q.data[em, :, vm], -1, 0)
+                am = np.moveaxis(aux.data[em, :, vm], -1, 0)
+                Gn = np.stack([n[d] * (lp - lm) / 2 for d in range(3)])
+                H = bl.transform_post_gradient_laplacian(Gn, Qm, am)
+                for s_ in range(bl.nhyper):
+                    cur = hg.data[em, s_, vm]
+                    hg.data[em, s_, vm] = cur + vMI * sM * H[s_]
 
     # ------------------------------------------------------------------
     # the tendency functor
@@ -414,8 +534,19 @@ class DGModel:
             self.update_auxiliary_state(Q, "ghost")   # after end_ghost_exchange!(Q)
             self.interface_gradients(Q, t, "exterior")
             ghost_exchange(self.state_gradient_flux)
+            if self.nhyper:
+                ghost_exchange(self.Qhypervisc_grad)
             if hasattr(bl, "update_auxiliary_state_gradient"):
                 bl.update_auxiliary_state_gradient(self, Q, "real")
+            if self.nhyper:
+                self.volume_divergence_of_gradients()
+                self.interface_divergence_of_gradients("interior")
+                self.interface_divergence_of_gradients("exterior")
+                ghost_exchange(self.Qhypervisc_div)
+                self.volume_gradients_of_laplacians(Q)
+                self.interface_gradients_of_laplacians(Q, "interior")
+                self.interface_gradients_of_laplacians(Q, "exterior")
+                ghost_exchange(self.Qhypervisc_grad)
         self.volume_tendency(tendency, Q, t, α, β)
         self.interface_tendency(tendency, Q, t, α, "interior")
         if second and hasattr(bl, "update_auxiliary_state_gradient"):
@@ -423,6 +554,24 @@ class DGModel:
         if not second:
             self.update_auxiliary_state(Q, "ghost")
         self.interface_tendency(tendency, Q, t, α, "exterior")
+
+
+def lengthscale_horizontal(g):
+    """``lengthscale_horizontal`` (src/Numerics/Mesh/Geometry.jl:129-152) at every node of the real
+    elements: mean of |J e1| and |J e2| times 2 / N, J = (d xi / d x)^-1."""
+    nr = g.nreal
+    vg = g.vgeo[:nr]
+    invJ = np.zeros((nr, g.Np, 3, 3), dtype=g.vgeo.dtype)
+    for i in range(3):
+        for j in range(3):
+            invJ[..., i, j] = vg[:, G._xi1x1 + 3 * j + i]      # d xi_{i+1} / d x_{j+1} (Grids.jl:76-92)
+    e = np.zeros((nr, g.Np, 3, 2), dtype=g.vgeo.dtype)
+    e[..., 0, 0] = 1
+    e[..., 1, 1] = 1
+    sol = np.linalg.solve(invJ, e)
+    Δ1 = np.sqrt((sol[..., 0] ** 2).sum(-1)) * 2 / g.N[0]
+    Δ2 = np.sqrt((sol[..., 1] ** 2).sum(-1)) * 2 / g.N[1]
+    return (Δ1 + Δ2) / 2
 
 
 def init_ode_state(dg, init_fn, t=0.0):
