@@ -15,6 +15,7 @@ TURB_CONSTANT_KINEMATIC, TURB_CONSTANT_DYNAMIC, TURB_SMAGORINSKY = 0, 1, 2
 SRC_GRAVITY, SRC_CORIOLIS, SRC_HELD_SUAREZ, SRC_RAYLEIGH_SPONGE = 1, 2, 4, 8
 BC_FREESLIP, BC_NOSLIP = 1, 2
 DIR_EVERY, DIR_HORIZONTAL, DIR_VERTICAL = 0, 1, 2
+HYPER_NONE, HYPER_DRY_BIHARMONIC = 0, 1
 FILTER_INDICES, FILTER_ATMOS_PERTURBATIONS = 0, 1
 COURANT_ADVECTIVE, COURANT_NONDIFFUSIVE, COURANT_DIFFUSIVE = 0, 1, 2
 
@@ -41,6 +42,7 @@ class cmdg_desc(C.Structure):
         ("sponge_z_max", C.c_double), ("sponge_z_sponge", C.c_double),
         ("sponge_alpha_max", C.c_double), ("sponge_gamma", C.c_double),
         ("sponge_u_relax", C.c_double * 3),
+        ("hyperdiffusion", C.c_int32), ("_pad0", C.c_int32), ("hyper_tau", C.c_double),
     ]
 
 

@@ -31,6 +31,9 @@ def aux_layout(m):
     if isinstance(m.turbulence, bl.SmagorinskyLilly):
         lay["Δ"] = c
         c += 1
+    if isinstance(m.hyperdiffusion, bl.DryBiharmonic):
+        lay["Δh"] = c
+        c += 1
     lay["θ_v"], lay["T"] = c, c + 1
     lay["A"] = c + 2
     return lay
@@ -142,6 +145,16 @@ def init_state_auxiliary(model, grid, exchange=None):
                - vg[:, 3] * (vg[:, 1] * vg[:, 8] - vg[:, 7] * vg[:, 2])
                + vg[:, 6] * (vg[:, 1] * vg[:, 5] - vg[:, 4] * vg[:, 2]))
         a[:nr, lay["Δ"]] = 2 / (torch.sign(det) * det.abs() ** (1.0 / 3.0) * max(1, grid.N))
+    if "Δh" in lay:
+        # lengthscale_horizontal (src/Numerics/Mesh/Geometry.jl:129-152): mean of |J e1|, |J e2| times 2 / N
+        vg = grid.vgeo[:nr].double()
+        invJ = torch.stack([torch.stack([vg[:, 3 * j + i] for j in range(3)], dim=-1) for i in range(3)], dim=-2)
+        e = torch.zeros(invJ.shape[:-1] + (2,), dtype=invJ.dtype, device=invJ.device)
+        e[..., 0, 0] = 1
+        e[..., 1, 1] = 1
+        sol = torch.linalg.solve(invJ, e)
+        Δ = (sol.pow(2).sum(dim=-2).sqrt() * 2 / max(1, grid.N)).mean(dim=-1)
+        a[:nr, lay["Δh"]] = Δ.to(a.dtype)
     ex(aux)
     return aux
 

@@ -105,6 +105,18 @@ class SmagorinskyLilly:
     C_smag: float = 0.21
 
 
+# --- hyperdiffusion (src/Common/TurbulenceClosures/TurbulenceClosures.jl:780-848) ----------
+class NoHyperDiffusion:
+    pass
+
+
+@dataclass(frozen=True)
+class DryBiharmonic:
+    """``DryBiharmonic{FT}(tau_timescale)``: fourth-order horizontal hyperdiffusion of u_h and h_tot
+    with nu4 = (Delta_h / 2)^4 / 2 / tau.  Needs ``diffusion_direction = HorizontalDirection()``."""
+    τ_timescale: float
+
+
 # --- sources ---------------------------------------------------------------
 class Gravity:
     pass
@@ -213,10 +225,15 @@ class AtmosModel:
 
     def number_states(self, kind):
         smag = isinstance(self.turbulence, SmagorinskyLilly)
+        hyp = isinstance(self.hyperdiffusion, DryBiharmonic)
         if kind == "Prognostic":
             return 5
         if kind == "Gradient":
-            return 5 if smag else 4
+            return (5 if smag else 4) + (4 if hyp else 0)
+        if kind == "GradientLaplacian":
+            return 4 if hyp else 0
+        if kind == "Hyperdiffusive":
+            return 12 if hyp else 0
         if kind == "GradientFlux":
             return 10 if smag else 9
         if kind == "Auxiliary":
@@ -227,11 +244,20 @@ class AtmosModel:
                 c += 7
             if smag:
                 c += 1
+            if hyp:
+                c += 1
             return c + 2
         raise KeyError(kind)
 
     def validate(self):
-        for name in ("hyperdiffusion", "precipitation", "radiation", "tracers", "turbconv"):
+        if self.hyperdiffusion is not None and \
+                not isinstance(self.hyperdiffusion, (NoHyperDiffusion, DryBiharmonic)):
+            raise UnsupportedModelError(
+                f"hyperdiffusion model {type(self.hyperdiffusion).__name__} is not supported by libcmdg "
+                "(NoHyperDiffusion / DryBiharmonic only)")
+        if isinstance(self.hyperdiffusion, DryBiharmonic) and isinstance(self.orientation, NoOrientation):
+            raise UnsupportedModelError("DryBiharmonic needs an orientation")
+        for name in ("precipitation", "radiation", "tracers", "turbconv"):
             if getattr(self, name) is not None:
                 raise UnsupportedModelError(
                     f"AtmosModel.{name} = {getattr(self, name)!r} is not supported by libcmdg "

@@ -98,6 +98,10 @@ struct cmdg_handle_s {
   // second-order path: diffusive flux per node (ghost part filled by the halo exchange) and its
   // normal component at every real element's own face nodes, written by the gradient kernel
   void *F2dev = nullptr, *FnDev = nullptr;
+  // DryBiharmonic: states_higher_order (create_states.jl:20-27), private: grad of (u_h, h_tot)
+  // (12 columns) and their horizontal Laplacians (4 columns)
+  bool hyper = false;
+  void *Qhg = nullptr, *Qhd = nullptr;
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
   bool grid_bound = false;
@@ -165,7 +169,8 @@ AtmosParams<R> make_params(const cmdg_handle_s *h) {
   for (int i = 0; i < 6; ++i) P.bc_kind[i] = d.bc_kind[i];
   // auxiliary layout, vars_state(::AtmosModel, ::Auxiliary) (AtmosModel.jl:479-497)
   int c = 3;
-  P.a_Phi = P.a_gradPhi = P.a_ref_rho = P.a_ref_p = P.a_Delta = -1;
+  P.a_Phi = P.a_gradPhi = P.a_ref_rho = P.a_ref_p = P.a_Delta = P.a_Delta_h = -1;
+  P.hyper_tau = (R)d.hyper_tau;
   if (d.orientation != CMDG_ORIENT_NONE) {
     P.a_Phi = c;
     P.a_gradPhi = c + 1;
@@ -177,6 +182,7 @@ AtmosParams<R> make_params(const cmdg_handle_s *h) {
     c += 7;
   }
   if (d.turbulence == CMDG_TURB_SMAGORINSKY) P.a_Delta = c++;
+  if (d.hyperdiffusion == CMDG_HYPER_DRY_BIHARMONIC) P.a_Delta_h = c++;
   P.a_theta_v = c;
   P.a_T = c + 1;
   P.naux = c + 2;
@@ -195,6 +201,7 @@ int expected_naux(const cmdg_desc &d) {
   if (d.orientation != CMDG_ORIENT_NONE) c += 4;
   if (d.ref_state == CMDG_REF_HYDROSTATIC) c += 7;
   if (d.turbulence == CMDG_TURB_SMAGORINSKY) c += 1;
+  if (d.hyperdiffusion == CMDG_HYPER_DRY_BIHARMONIC) c += 1;
   return c + 2;
 }
 
@@ -270,18 +277,138 @@ int launch_tendency(cmdg_handle h, const TendArgs<R> &a, int64_t n, cudaStream_t
   return fail(h, CMDG_ERR_UNSUPPORTED, "unsupported first-order numerical flux");
 }
 
+template <class R, bool AUX, bool HYPER>
+int launch_gradient_inst(cmdg_handle h, const GradArgs<R> &a, const AtmosParams<R> &P, int64_t n,
+                         cudaStream_t st) {
+  using SM = GradSmem<R, 5, AUX, HYPER>;
+  auto kern = dg_gradient_kernel<R, 5, AUX, HYPER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    attr_set = true;
+  }
+  kern<<<(unsigned)n, Dims<5>::BLOCK, sizeof(SM), st>>>(a, P);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
 template <class R>
 int launch_gradient(cmdg_handle h, const GradArgs<R> &a, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   if (int rc = ensure_const_D<R>(h, st)) return rc;
   const AtmosParams<R> P = make_params<R>(h);
-  if (h->aux_model)
-    dg_gradient_kernel<R, 5, true><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
-  else
-    dg_gradient_kernel<R, 5, false><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  if (h->hyper) return launch_gradient_inst<R, true, true>(h, a, P, n, st);
+  if (h->aux_model) return launch_gradient_inst<R, true, false>(h, a, P, n, st);
+  return launch_gradient_inst<R, false, false>(h, a, P, n, st);
+}
+
+template <class R> int exchange_begin_t(cmdg_handle h, void *array, int nstate, cudaStream_t st);
+template <class R> int exchange_end_t(cmdg_handle h, void *array, int nstate, cudaStream_t st);
+
+// DryBiharmonic passes 2 and 3 (hyper_divergence_kernel, hyper_flux_kernel)
+template <class R>
+HyperArgs<R> hyper_args(cmdg_handle h, const void *Q) {
+  HyperArgs<R> a{};
+  a.Q = (const R *)Q;
+  a.aux = (const R *)h->aux;
+  a.gradflux = (const R *)h->gradflux;
+  a.vgeoP = (const R *)h->vgeoP;
+  a.sgeoP = (const R *)h->sgeoP;
+  a.conn = h->conn;
+  a.Qhg = (R *)h->Qhg;
+  a.Qhd = (R *)h->Qhd;
+  a.F2 = (R *)h->F2dev;
+  a.Fn = (R *)h->FnDev;
+  return a;
+}
+template <class R>
+int launch_hyper(cmdg_handle h, int pass, const HyperArgs<R> &a, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (int rc = ensure_const_D<R>(h, st)) return rc;
+  if (pass == 2) {
+    hyper_divergence_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a);
+  } else {
+    const AtmosParams<R> P = make_params<R>(h);
+    hyper_flux_kernel<R, 5, true><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  }
   CU(cudaGetLastError());
   h->launches++;
   return 0;
+}
+
+// Everything between the state exchange and the tendency kernel on the second-order path: gradient
+// kernel (+ the two hyperdiffusion passes with their exchanges), leaving F2 / Fn ready and the F2
+// halo in flight (`first`/`second` = the launch lists processed before / after each exchange starts;
+// the reference order is interior-first, the fused stepper's exterior-first).
+template <class R>
+int second_order_passes(cmdg_handle h, GradArgs<R> ga, const void *Q, bool par, bool exterior_first,
+                        bool q_exchange_open, cudaStream_t st) {
+  int rc;
+  const int64_t nreal = h->d.nrealelem;
+  if (!par) {
+    ga.elems = nullptr;
+    if ((rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+    if (h->hyper) {
+      HyperArgs<R> ha = hyper_args<R>(h, Q);
+      if ((rc = launch_hyper<R>(h, 2, ha, nreal, st))) return rc;
+      if ((rc = launch_hyper<R>(h, 3, ha, nreal, st))) return rc;
+    }
+    return 0;
+  }
+  const int *ext = h->exterior, *inr = h->interior;
+  const int64_t next = h->nexterior, ninr = h->ninterior;
+  void *Qv = const_cast<void *>(Q);
+  if (exterior_first) {
+    // ghosts of Q are already in place
+    ga.elems = ext;
+    if ((rc = launch_gradient<R>(h, ga, next, st))) return rc;
+    if (!h->hyper) {
+      if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
+      ga.elems = inr;
+      if ((rc = launch_gradient<R>(h, ga, ninr, st))) return rc;
+      return exchange_end_t<R>(h, h->F2dev, 12, st);
+    }
+    if ((rc = exchange_begin_t<R>(h, h->Qhg, 12, st))) return rc;
+    ga.elems = inr;
+    if ((rc = launch_gradient<R>(h, ga, ninr, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, h->Qhg, 12, st))) return rc;
+    HyperArgs<R> ha = hyper_args<R>(h, Q);
+    ha.elems = ext;
+    if ((rc = launch_hyper<R>(h, 2, ha, next, st))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->Qhd, 4, st))) return rc;
+    ha.elems = inr;
+    if ((rc = launch_hyper<R>(h, 2, ha, ninr, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, h->Qhd, 4, st))) return rc;
+    ha.elems = ext;
+    if ((rc = launch_hyper<R>(h, 3, ha, next, st))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
+    ha.elems = inr;
+    if ((rc = launch_hyper<R>(h, 3, ha, ninr, st))) return rc;
+    return exchange_end_t<R>(h, h->F2dev, 12, st);
+  }
+  // reference order (DGModel.jl:125-310): interior while the Q halo is in flight, then exterior
+  ga.elems = inr;
+  if ((rc = launch_gradient<R>(h, ga, ninr, st))) return rc;
+  if (q_exchange_open && (rc = exchange_end_t<R>(h, Qv, h->d.nstate, st))) return rc;
+  ga.elems = ext;
+  if ((rc = launch_gradient<R>(h, ga, next, st))) return rc;
+  if (h->hyper) {
+    HyperArgs<R> ha = hyper_args<R>(h, Q);
+    if ((rc = exchange_begin_t<R>(h, h->Qhg, 12, st))) return rc;
+    ha.elems = inr;
+    if ((rc = launch_hyper<R>(h, 2, ha, ninr, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, h->Qhg, 12, st))) return rc;
+    ha.elems = ext;
+    if ((rc = launch_hyper<R>(h, 2, ha, next, st))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->Qhd, 4, st))) return rc;
+    ha.elems = inr;
+    if ((rc = launch_hyper<R>(h, 3, ha, ninr, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, h->Qhd, 4, st))) return rc;
+    ha.elems = ext;
+    if ((rc = launch_hyper<R>(h, 3, ha, next, st))) return rc;
+  }
+  return exchange_begin_t<R>(h, h->F2dev, 12, st);   // ended by the caller after the interior tendency
 }
 
 // ------------------------------------------------------------------------------------
@@ -474,25 +601,16 @@ int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double 
   a.beta = (R)beta;
   a.t = (R)t;
   GradArgs<R> ga{(const R *)Q, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
-                 (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev};
+                 (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev,
+                 (R *)h->Qhg};
   int rc;
   if (!par) {
-    if (h->visc) {
-      ga.elems = nullptr;
-      if ((rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
-    }
+    if (h->visc && (rc = second_order_passes<R>(h, ga, Q, false, false, false, st))) return rc;
     a.elems = nullptr;
     return launch_tendency<R>(h, a, nreal, st);
   }
   if ((rc = exchange_begin_t<R>(h, Q, h->d.nstate, st))) return rc;
-  if (h->visc) {
-    ga.elems = h->interior;
-    if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
-    if ((rc = exchange_end_t<R>(h, Q, h->d.nstate, st))) return rc;
-    ga.elems = h->exterior;
-    if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
-    if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
-  }
+  if (h->visc && (rc = second_order_passes<R>(h, ga, Q, true, false, true, st))) return rc;
   a.elems = h->interior;
   if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
   if (h->visc) {
@@ -595,21 +713,15 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       // aux diagnostics are refreshed by the last stage only (they are read after steps)
       if (s != nstage - 1) a.aux_out = nullptr;
       GradArgs<R> ga{cur, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
-                     (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev};
+                     (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev,
+                     (R *)h->Qhg};
       int rc;
       if (!par) {
-        if (h->visc && (rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+        if (h->visc && (rc = second_order_passes<R>(h, ga, cur, false, true, false, st))) return rc;
         a.elems = nullptr;
         if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
       } else {
-        if (h->visc) {
-          ga.elems = h->exterior;
-          if ((rc = launch_gradient<R>(h, ga, h->nexterior, st))) return rc;
-          if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
-          ga.elems = h->interior;
-          if ((rc = launch_gradient<R>(h, ga, h->ninterior, st))) return rc;
-          if ((rc = exchange_end_t<R>(h, h->F2dev, 12, st))) return rc;
-        }
+        if (h->visc && (rc = second_order_passes<R>(h, ga, cur, true, true, false, st))) return rc;
         // a per-step filter changes the new state after the last stage: its halo goes out after
         // the filter instead of overlapping the interior kernel
         const bool filt_now = h->step_filter_target >= 0 && s == nstage - 1;
@@ -864,7 +976,16 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (d->naux != expected_naux(*d))
     return fail(nullptr, CMDG_ERR_INVALID, "naux does not match the model's auxiliary state");
   const int gf = d->turbulence == CMDG_TURB_SMAGORINSKY ? 10 : 9;
-  if (d->ngradflux != gf || d->ngrad != (gf == 10 ? 5 : 4))
+  if (d->hyperdiffusion != CMDG_HYPER_NONE && d->hyperdiffusion != CMDG_HYPER_DRY_BIHARMONIC)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported hyperdiffusion model");
+  const int hyp = d->hyperdiffusion == CMDG_HYPER_DRY_BIHARMONIC;
+  if (hyp && d->orientation == CMDG_ORIENT_NONE)
+    return fail(nullptr, CMDG_ERR_INVALID, "DryBiharmonic needs an orientation");
+  if (hyp && d->diffusion_direction != CMDG_DIR_HORIZONTAL)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED,
+                "DryBiharmonic: only diffusion_direction = HorizontalDirection() (the reference's 3-D EveryDirection kernel does not run)");
+  if (hyp && !(d->hyper_tau > 0)) return fail(nullptr, CMDG_ERR_INVALID, "DryBiharmonic needs hyper_tau > 0");
+  if (d->ngradflux != gf || d->ngrad != (gf == 10 ? 5 : 4) + 4 * hyp)
     return fail(nullptr, CMDG_ERR_INVALID, "ngrad/ngradflux do not match the model");
   if (d->nrealelem < 0 || d->nelem < d->nrealelem || d->nelem > 0x7fffffffLL)
     return fail(nullptr, CMDG_ERR_INVALID, "bad element counts");
@@ -879,7 +1000,8 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   h->fb = d->float_bytes;
   h->aux_model = d->orientation != CMDG_ORIENT_NONE || d->ref_state != CMDG_REF_NONE;
   const bool zero_visc = d->turbulence != CMDG_TURB_SMAGORINSKY && d->turb_param == 0.0;
-  h->visc = !(d->skip_zero_viscosity && zero_visc);
+  h->visc = !(d->skip_zero_viscosity && zero_visc) || hyp;
+  h->hyper = hyp;
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
   cudaError_t e1 = cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
   cudaError_t e2 = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
@@ -898,7 +1020,7 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev};
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -1008,6 +1130,13 @@ int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
     CU(cudaMalloc(&h->FnDev, fn + 16));
     CU(cudaMemset(h->F2dev, 0, f2));
     CU(cudaMemset(h->FnDev, 0, fn));
+    if (h->hyper) {
+      const size_t hd = (size_t)h->d.nelem * 4 * h->Np * h->fb;
+      CU(cudaMalloc(&h->Qhg, f2 + 16));
+      CU(cudaMalloc(&h->Qhd, hd + 16));
+      CU(cudaMemset(h->Qhg, 0, f2));
+      CU(cudaMemset(h->Qhd, 0, hd));
+    }
   }
   return CMDG_OK;
 }

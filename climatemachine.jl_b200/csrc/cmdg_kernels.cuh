@@ -50,7 +50,8 @@ struct AtmosParams {
   int horizontal_diffusion;
   int bc_kind[6];
   // auxiliary-state column ids (0-based), -1 when absent
-  int a_Phi, a_gradPhi, a_ref_rho, a_ref_p, a_Delta, a_theta_v, a_T;
+  int a_Phi, a_gradPhi, a_ref_rho, a_ref_p, a_Delta, a_Delta_h, a_theta_v, a_T;
+  R hyper_tau;   // DryBiharmonic time scale (a_Delta_h >= 0 when hyperdiffusion is on)
   int naux, ngradflux;
   // HeldSuarezForcing / RayleighSponge (SRCX kernels only)
   R inv_day, sponge_z_max, sponge_z_sponge, sponge_alpha_max, sponge_gamma, sponge_u[3];
@@ -1014,6 +1015,8 @@ struct GradArgs {
   // the element's own face nodes (NULL = not wanted)
   R *F2;   // [nelem][12][Np]
   R *Fn;   // [nreal][6*Nfp][4]
+  // DryBiharmonic (HYPER kernels): gradient of (u_h, h_tot), column 3*s + d  [nelem][12][Np]
+  R *Qhg;
 };
 
 template <class R>
@@ -1052,16 +1055,37 @@ __device__ __forceinline__ void gradient_flux(const AtmosParams<R> &P, const R d
 #ifndef CMDG_GRAD_MINBLOCKS
 #define CMDG_GRAD_MINBLOCKS 5
 #endif
-template <class R, int NQ, bool AUX>
-__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? CMDG_GRAD_MINBLOCKS : 1))
+// HYPER (DryBiharmonic, TurbulenceClosures.jl:793-848): the gradient argument grows by
+// u_h = (I - k k') u and h_tot (compute_gradient_argument!, :813-826); their horizontal gradients
+// (volume + central face term, DGModel_kernels.jl:1081-1098, 1618-1628) go to Qhg.  grad h_tot is
+// the first three gradient-flux columns, so only u_h costs extra contractions.  The diffusive flux is
+// then assembled by hyper_flux_kernel, not here.
+template <class R, int NQ, bool AUX, bool HYPER>
+struct GradSmem {
+  static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
+  R G[5][NP];
+  R Q[5][NP];
+  R Phi[AUX ? NP : 1];
+  R Face[10][NFN];
+  R Qp[6][NFN];                       // neighbour traces (Q+, Phi+), gathered asynchronously
+  R Uh[HYPER ? 3 : 1][HYPER ? NP : 1];     // u_h at my nodes
+  R K[HYPER ? 3 : 1][HYPER ? NP : 1];      // k = grad Phi / grav at my nodes
+  R Kp[HYPER ? 3 : 1][HYPER ? NFN : 1];    // neighbour grad Phi
+  R FaceH[HYPER ? 9 : 1][HYPER ? NFN : 1]; // face terms of grad u_h
+};
+
+template <class R, int NQ, bool AUX, bool HYPER>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (HYPER ? 3 : CMDG_GRAD_MINBLOCKS) : 1))
 dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
-  __shared__ R sG[5][NP];
-  __shared__ R sQ[5][NP];
-  __shared__ R sPhi[AUX ? NP : 1];
-  __shared__ R sFace[10][NFN];
-  __shared__ R sQp[6][NFN];      // neighbour traces (Q+, Phi+), gathered asynchronously
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GradSmem<R, NQ, AUX, HYPER> &S = *reinterpret_cast<GradSmem<R, NQ, AUX, HYPER> *>(smem_raw);
+  R(&sG)[5][NP] = S.G;
+  R(&sQ)[5][NP] = S.Q;
+  R(&sPhi)[AUX ? NP : 1] = S.Phi;
+  R(&sFace)[10][NFN] = S.Face;
+  R(&sQp)[6][NFN] = S.Qp;
   constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
@@ -1090,15 +1114,23 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&sQp[s][it], A.Q + offp + (size_t)s * NP);
       if (AUX && P.a_Phi >= 0)
         cp_async<sizeof(R)>(&sQp[5][it], A.aux + (size_t)cn[r].x * P.naux * NP + (size_t)P.a_Phi * NP + vp);
+      if (HYPER) {
+        // the neighbour's own grad Phi (element-local derivative: differs from mine at truncation level)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          cp_async<sizeof(R)>(&S.Kp[HYPER ? d : 0][HYPER ? it : 0],
+                              A.aux + (size_t)cn[r].x * P.naux * NP + (size_t)(P.a_gradPhi + d) * NP + vp);
+      }
     }
   }
 
   R q[5] = {1, 0, 0, 0, 0}, G[5], Phi = 0, gPhi[3] = {0, 0, 0};
+  const R inv_grav = R(1) / P.grav;
   if (tid < NP) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = A.Q[eoffQ + (size_t)s * NP + tid];
     if (AUX && P.a_Phi >= 0) Phi = A.aux[eoffA + (size_t)P.a_Phi * NP + tid];
-    if (AUX && P.a_gradPhi >= 0 && P.turbulence == TURB_SMAGORINSKY) {
+    if (AUX && P.a_gradPhi >= 0 && (HYPER || P.turbulence == TURB_SMAGORINSKY)) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
     }
@@ -1109,6 +1141,15 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       sQ[s][tid] = q[s];
     }
     if (AUX) sPhi[tid] = Phi;
+    if (HYPER) {
+      const R k[3] = {gPhi[0] * inv_grav, gPhi[1] * inv_grav, gPhi[2] * inv_grav};
+      const R ku = k[0] * G[0] + k[1] * G[1] + k[2] * G[2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        S.K[HYPER ? d : 0][HYPER ? tid : 0] = k[d];
+        S.Uh[HYPER ? d : 0][HYPER ? tid : 0] = G[d] - k[d] * ku;
+      }
+    }
   }
   __syncthreads();
 
@@ -1136,12 +1177,24 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) gPm[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + vm];
     }
+    R uhm[3] = {0, 0, 0}, dUh[3] = {0, 0, 0};
+    if (HYPER) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) uhm[d] = S.Uh[HYPER ? d : 0][HYPER ? vm : 0];
+    }
     if (bctag == 0) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) qp[s] = sQp[s][it];
       R Phip = 0;
       if (AUX && P.a_Phi >= 0) Phip = sQp[5][it];
       gradient_argument<R>(P, qp, Phip, Gs);
+      if (HYPER) {
+        const R kp[3] = {S.Kp[0][HYPER ? it : 0] * inv_grav, S.Kp[HYPER ? 1 : 0][HYPER ? it : 0] * inv_grav,
+                         S.Kp[HYPER ? 2 : 0][HYPER ? it : 0] * inv_grav};
+        const R ku = kp[0] * Gs[0] + kp[1] * Gs[1] + kp[2] * Gs[2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dUh[d] = R(0.5) * ((Gs[d] - kp[d] * ku) + uhm[d]) - uhm[d];
+      }
 #pragma unroll
       for (int s = 0; s < 5; ++s) Gs[s] = R(0.5) * (Gs[s] + Gm[s]) - Gm[s];
     } else {
@@ -1158,8 +1211,21 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
         qp[1] = qp[2] = qp[3] = R(0);
       }
       gradient_argument<R>(P, qp, Phim, Gs);
+      if (HYPER) {
+        // the boundary state keeps the minus-side auxiliary state: same k
+        const R km[3] = {S.K[0][HYPER ? vm : 0], S.K[HYPER ? 1 : 0][HYPER ? vm : 0], S.K[HYPER ? 2 : 0][HYPER ? vm : 0]};
+        const R ku = km[0] * Gs[0] + km[1] * Gs[1] + km[2] * Gs[2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dUh[d] = (Gs[d] - km[d] * ku) - uhm[d];
+      }
 #pragma unroll
       for (int s = 0; s < 5; ++s) Gs[s] -= Gm[s];
+    }
+    if (HYPER) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) S.FaceH[HYPER ? 3 * c + d : 0][HYPER ? it : 0] = sMvMI * (n[d] * dUh[c]);
     }
     R dG[3][5];
 #pragma unroll
@@ -1174,6 +1240,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
 
   // volume: strong-form gradient  xi_x * (D G)
   R gfv[10];
+  R hgv[HYPER ? 9 : 1];
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   if (tid < NP) {
     R g[9], MI;
@@ -1200,6 +1267,24 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 5; ++s)
         dG[d][s] = g[d] * G1[s] + g[3 + d] * G2[s] + vfac * (g[6 + d] * G3[s]);
     gradient_flux<R>(P, dG, gPhi, G[4], gfv);
+    if (HYPER) {
+      // horizontal gradient of u_h (the diffusion direction is horizontal with DryBiharmonic)
+      R H1[3] = {0, 0, 0}, H2[3] = {0, 0, 0};
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) {
+        const R d1 = const_D<R>(i * NQ + n), d2 = const_D<R>(j * NQ + n);
+        const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          H1[c] += d1 * S.Uh[HYPER ? c : 0][HYPER ? o1 : 0];
+          H2[c] += d2 * S.Uh[HYPER ? c : 0][HYPER ? o2 : 0];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) hgv[3 * c + d] = g[d] * H1[c] + g[3 + d] * H2[c];
+    }
   }
   __syncthreads();
   if (tid < NP) {
@@ -1218,8 +1303,23 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][5 * NFP + i + NQ * j];
     const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
     for (int s = 0; s < P.ngradflux; ++s) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
+    if (HYPER) {
+      const int fi[2] = {(i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1),
+                         (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1)};
+#pragma unroll
+      for (int f2 = 0; f2 < 2; ++f2)
+        if (fi[f2] >= 0) {
+#pragma unroll
+          for (int c = 0; c < 9; ++c) hgv[c] += S.FaceH[HYPER ? c : 0][HYPER ? fi[f2] : 0];
+        }
+      const size_t eoffH = (size_t)e * 12 * NP + tid;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) A.Qhg[eoffH + (size_t)c * NP] = hgv[c];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) A.Qhg[eoffH + (size_t)(9 + d) * NP] = gfv[d];
+    }
   }
-  if (!A.F2) return;
+  if (HYPER || !A.F2) return;
   // ---- second-order flux F2(Q, GF, aux) of this node, once (flux_second_order!, kernels.jl:84-105):
   // the tendency kernel then needs no closure evaluation, neither in the volume nor on faces.
   // F2 goes to global memory (volume term, ghost exchange) and, through shared memory, into
@@ -1232,6 +1332,274 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
     if (AUX && P.a_Delta >= 0) Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
     R F2[3][5];
     flux_second_order<R>(P, q, gfv, gPhi, Delta, F2);
+    const size_t eoffF = (size_t)e * 12 * NP + tid;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int c = 1; c < 5; ++c) {
+        A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
+        sF2[4 * d + c - 1][tid] = F2[d][c];
+      }
+  }
+  __syncthreads();
+  for (int it = tid; it < NFN; it += BLOCK) {
+    const int f = it / NFP, fn = it - f * NFP;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    R n[3], sMvMI;
+    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
+    typename Vec2<R>::type o0, o1;
+    o0.x = n[0] * sF2[0][vm] + n[1] * sF2[4][vm] + n[2] * sF2[8][vm];
+    o0.y = n[0] * sF2[1][vm] + n[1] * sF2[5][vm] + n[2] * sF2[9][vm];
+    o1.x = n[0] * sF2[2][vm] + n[1] * sF2[6][vm] + n[2] * sF2[10][vm];
+    o1.y = n[0] * sF2[3][vm] + n[1] * sF2[7][vm] + n[2] * sF2[11][vm];
+    typename Vec2<R>::type *po = reinterpret_cast<typename Vec2<R>::type *>(A.Fn + ((size_t)e * NFN + it) * 4);
+    po[0] = o0;
+    po[1] = o1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// DryBiharmonic hyperdiffusion, horizontal direction (schedule DGModel.jl:226-310).  The reference
+// runs volume_divergence_of_gradients! (DGModel_kernels.jl:2132-2228) + interface_divergence_of_
+// gradients! (:2359-2490, CentralNumericalFluxDivergence, NumericalFluxes.jl:716-770), then
+// volume_gradients_of_laplacians! (:2521-2680) + interface_gradients_of_laplacians! (:2860-3026,
+// CentralNumericalFluxHigherOrder, NumericalFluxes.jl:772-835) and evaluates flux_second_order!
+// of the hyperdiffusive state again in the volume and on both sides of every face.  Here: one
+// kernel per pass (volume + the four horizontal faces fused per element), and the second one
+// finishes with the TOTAL diffusive flux F2 = F2(viscous) + F2(hyper) per node plus its normal
+// component at the element's own face nodes, which is all the tendency kernel consumes -- the
+// hyperdiffusive state itself never goes to memory and its halo exchange is replaced by the F2 one.
+// ---------------------------------------------------------------------------------------
+template <class R>
+struct HyperArgs {
+  const R *Q, *aux, *gradflux;
+  const R *vgeoP, *sgeoP;
+  const int2 *conn;
+  const int *elems;
+  R *Qhg;   // [nelem][12][Np] gradients, column 3*s + d (s: u_h1..3, h_tot)
+  R *Qhd;   // [nelem][4][Np]  horizontal Laplacians
+  R *F2;    // [nelem][12][Np]
+  R *Fn;    // [nreal][6*Nfp][4]
+};
+
+// Qhd[s] = -MI D^T (M xi_h . grad G_s) + sum_{f<4} vMI sM (grad+ + grad-) . n / 2
+template <class R, int NQ>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
+hyper_divergence_kernel(const HyperArgs<R> A) {
+  constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
+  constexpr int BLOCK = Dims<NQ>::BLOCK, NH = 4 * NFP;
+  static_assert(NH <= BLOCK, "one horizontal face node per thread");
+  __shared__ R sGr[12][NP];     // my gradients
+  __shared__ R sS[2][4][NP];    // M xi_m . grad G_s, m = 1, 2
+  __shared__ R sGp[12][NH];     // neighbour gradients at my horizontal face nodes
+  __shared__ R sFace[4][NH];
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  int2 cn = make_int2(0, 16);
+  if (tid < NH) {
+    cn = A.conn[(size_t)e * 6 + tid / NFP];
+    if (((cn.y >> 4) & 15) == 0) {
+      const int fn = tid % NFP;
+      int a = fn % NQ;
+      const int b = fn / NQ;
+      if (cn.y & 8) a = NQ - 1 - a;
+      const int vp = face_to_vol<NQ>(cn.y & 7, a, b);
+      const R *pg = A.Qhg + (size_t)cn.x * 12 * NP + vp;
+#pragma unroll
+      for (int c = 0; c < 12; ++c) cp_async<sizeof(R)>(&sGp[c][tid], pg + (size_t)c * NP);
+    }
+  }
+  R MI = 0;
+  if (tid < NP) {
+    R g[9], gr[12];
+    const size_t eo = (size_t)e * 12 * NP + tid;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) gr[c] = A.Qhg[eo + (size_t)c * NP];
+    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) sGr[c][tid] = gr[c];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        sS[m][s][tid] = g[3 * m] * gr[3 * s] + g[3 * m + 1] * gr[3 * s + 1] + g[3 * m + 2] * gr[3 * s + 2];
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (tid < NH) {
+    const int f = tid / NFP, fn = tid - f * NFP;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    const bool wall = ((cn.y >> 4) & 15) != 0;
+    R n[3], sMvMI;
+    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + tid) * 4, n, sMvMI);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      R l = R(0);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const R gm = sGr[3 * s + d][vm];
+        // walls: boundary_state! of the divergence flux is a no-op, grad+ = grad-
+        const R gp = wall ? gm : sGp[3 * s + d][tid];
+        l += (gp + gm) * (n[d] * R(0.5));
+      }
+      sFace[s][tid] = sMvMI * l;
+    }
+  }
+  R div[4] = {0, 0, 0, 0};
+  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
+  if (tid < NP) {
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const R d1 = const_D<R>(n * NQ + i), d2 = const_D<R>(n * NQ + j);
+      const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) div[s] += d1 * sS[0][s][o1] + d2 * sS[1][s][o2];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) div[s] *= -MI;
+  }
+  __syncthreads();
+  if (tid < NP) {
+    const int f1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
+    const int f2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
+    if (f1 >= 0) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) div[s] += sFace[s][f1];
+    }
+    if (f2 >= 0) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) div[s] += sFace[s][f2];
+    }
+    const size_t eo = (size_t)e * 4 * NP + tid;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) A.Qhd[eo + (size_t)s * NP] = div[s];
+  }
+}
+
+// H[3 s + d] = nu4 (xi_h,d D lap_s) + sum_{f<4} vMI sM nu4 n_d (lap+ - lap-) / 2
+// (transform_post_gradient_laplacian!, TurbulenceClosures.jl:828-848: nu4 = (Delta_h / 2)^4 / 2 / tau),
+// then F2 = flux_second_order(viscous) + HyperdiffViscousFlux / HyperdiffEnthalpyFlux
+// (tendencies_momentum.jl:51-54, tendencies_energy.jl:40-48) and Fn = n . F2 on my faces.
+template <class R, int NQ, bool AUX>
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
+hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
+  constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
+  constexpr int BLOCK = Dims<NQ>::BLOCK, NH = 4 * NFP;
+  __shared__ R sL[4][NP];
+  __shared__ R sNu[NP];
+  __shared__ R sLp[4][NH];
+  __shared__ R sBuf[12 * NP];   // face terms [12][NH] first, then F2 [12][NP]
+  static_assert(12 * NH <= 12 * NP, "face terms fit the F2 staging buffer");
+  R(*sFace)[NH] = reinterpret_cast<R(*)[NH]>(sBuf);
+  R(*sF2)[NP] = reinterpret_cast<R(*)[NP]>(sBuf);
+  const int tid = threadIdx.x;
+  const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
+  const size_t eoffA = (size_t)e * P.naux * NP;
+  int2 cn = make_int2(0, 16);
+  if (tid < NH) {
+    cn = A.conn[(size_t)e * 6 + tid / NFP];
+    if (((cn.y >> 4) & 15) == 0) {
+      const int fn = tid % NFP;
+      int a = fn % NQ;
+      const int b = fn / NQ;
+      if (cn.y & 8) a = NQ - 1 - a;
+      const int vp = face_to_vol<NQ>(cn.y & 7, a, b);
+      const R *pl = A.Qhd + (size_t)cn.x * 4 * NP + vp;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) cp_async<sizeof(R)>(&sLp[s][tid], pl + (size_t)s * NP);
+    }
+  }
+  R q[5] = {1, 0, 0, 0, 0}, g[9], MI = 0, nu4 = 0;
+  if (tid < NP) {
+    const size_t eo = (size_t)e * 4 * NP + tid;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) sL[s][tid] = A.Qhd[eo + (size_t)s * NP];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) q[s] = A.Q[(size_t)e * 5 * NP + (size_t)s * NP + tid];
+    const R hD = A.aux[eoffA + (size_t)P.a_Delta_h * NP + tid] * R(0.5);
+    const R hD2 = hD * hD;
+    nu4 = hD2 * hD2 / R(2) / P.hyper_tau;
+    sNu[tid] = nu4;
+    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (tid < NH) {
+    const int f = tid / NFP, fn = tid - f * NFP;
+    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    const bool wall = ((cn.y >> 4) & 15) != 0;
+    R n[3], sMvMI;
+    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + tid) * 4, n, sMvMI);
+    const R w = sMvMI * sNu[vm];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      // walls: lap+ = lap- (no boundary flux of the Laplacian)
+      const R dl = wall ? R(0) : (sLp[s][tid] - sL[s][vm]) * R(0.5);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sFace[3 * s + d][tid] = w * (n[d] * dl);
+    }
+  }
+  R H[12];
+  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
+  if (tid < NP) {
+    R L1[4] = {0, 0, 0, 0}, L2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const R d1 = const_D<R>(i * NQ + n), d2 = const_D<R>(j * NQ + n);
+      const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        L1[s] += d1 * sL[s][o1];
+        L2[s] += d2 * sL[s][o2];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) H[3 * s + d] = nu4 * ((MI * g[d]) * L1[s] + (MI * g[3 + d]) * L2[s]);
+  }
+  __syncthreads();
+  R F2[3][5];
+  if (tid < NP) {
+    const int f1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
+    const int f2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
+    if (f1 >= 0) {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) H[c] += sFace[c][f1];
+    }
+    if (f2 >= 0) {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) H[c] += sFace[c][f2];
+    }
+    // viscous part (skipped when the closure is identically zero, as in the GCM drivers'
+    // ConstantKinematicViscosity(0))
+    const bool viscous = P.turbulence == TURB_SMAGORINSKY || P.turb_param != R(0);
+    if (viscous) {
+      R gf[10], gPhi[3] = {0, 0, 0}, Delta = R(0);
+      const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+#pragma unroll
+      for (int s = 0; s < 10; ++s) gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
+      if (AUX && P.turbulence == TURB_SMAGORINSKY) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
+        Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
+      }
+      flux_second_order<R>(P, q, gf, gPhi, Delta, F2);
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) F2[d][c] = R(0);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) F2[d][1 + c] += q[0] * H[d + 3 * c];
+      F2[d][4] += (H[d] * q[1] + H[d + 3] * q[2] + H[d + 6] * q[3]) + H[9 + d] * q[0];
+    }
+  }
+  __syncthreads();   // face terms consumed: the buffer now stages F2
+  if (tid < NP) {
     const size_t eoffF = (size_t)e * 12 * NP + tid;
 #pragma unroll
     for (int d = 0; d < 3; ++d)

@@ -178,6 +178,10 @@ class DGModel:
                     d.sponge_u_relax[i] = s.u_relaxation[i]
         d.diffusion_direction = (_lib.DIR_HORIZONTAL if isinstance(self.diffusion_direction, bl.HorizontalDirection)
                                  else _lib.DIR_EVERY)
+        if isinstance(m.hyperdiffusion, bl.DryBiharmonic):
+            d.hyperdiffusion, d.hyper_tau = _lib.HYPER_DRY_BIHARMONIC, float(m.hyperdiffusion.τ_timescale)
+        else:
+            d.hyperdiffusion = _lib.HYPER_NONE
         d.skip_zero_viscosity = int(skip_zero_viscosity)
         d.write_aux_diagnostics = int(write_aux_diagnostics)
         d.nbc = len(m.boundaryconditions)

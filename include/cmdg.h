@@ -61,6 +61,8 @@ enum { CMDG_TURB_CONSTANT_KINEMATIC = 0, CMDG_TURB_CONSTANT_DYNAMIC = 1, CMDG_TU
 enum { CMDG_SRC_GRAVITY = 1, CMDG_SRC_CORIOLIS = 2, CMDG_SRC_HELD_SUAREZ = 4, CMDG_SRC_RAYLEIGH_SPONGE = 8 };
 /* src/Atmos/Model/bc_momentum.jl:1-80 with Insulating energy (bc_energy.jl:10-17) */
 enum { CMDG_BC_FREESLIP = 1, CMDG_BC_NOSLIP = 2 };
+/* hyperdiffusion model (src/Common/TurbulenceClosures/TurbulenceClosures.jl:793-848) */
+enum { CMDG_HYPER_NONE = 0, CMDG_HYPER_DRY_BIHARMONIC = 1 };
 /* DGModel.direction / diffusion_direction (src/Numerics/DGMethods/DGModel.jl:3-19) */
 enum { CMDG_DIR_EVERY = 0, CMDG_DIR_HORIZONTAL = 1 };
 
@@ -104,6 +106,12 @@ typedef struct {
   double day;             /* CLIMAParameters.Planet.day (HeldSuarezForcing rates) */
   /* RayleighSponge{FT}(z_max, z_sponge, alpha_max, u_relaxation, gamma) */
   double sponge_z_max, sponge_z_sponge, sponge_alpha_max, sponge_gamma, sponge_u_relax[3];
+  /* DryBiharmonic{FT}(tau_timescale): needs diffusion_direction = CMDG_DIR_HORIZONTAL (the
+   * reference's 3-D EveryDirection kernel does not run, DGModel_kernels.jl:2640-2650) and adds
+   * aux.hyperdiffusion.Delta after aux.turbulence.Delta; ngrad grows by 4 (u_h, h_tot) */
+  int32_t hyperdiffusion; /* CMDG_HYPER_* */
+  int32_t _pad0;
+  double hyper_tau;
 } cmdg_desc;
 
 /*

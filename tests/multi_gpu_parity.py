@@ -94,6 +94,12 @@ def main():
     Q0s = [oatmos.init_baroclinic_wave(model, np.moveaxis(a.data[:g.nreal], 1, 0))
            for g, a in zip(gs, tmp.state_auxiliary)]
     run_case("held_suarez_like", model, gs, Q0s, "rusanov", 0.5, 2, rank, world, False, "horizontal")
+    # DryBiharmonic hyperdiffusion: four exchanges per evaluation (Q, grad, Laplacian, total F2)
+    model, gs = parity.gcm_setup(3, 2, csize=world, hyperdiffusion=("dry_biharmonic", 8 * 3600.0))
+    tmp = odg.DGModel(model, gs, "rusanov", diffusion_direction="horizontal")
+    Q0s = [oatmos.init_baroclinic_wave(model, np.moveaxis(a.data[:g.nreal], 1, 0))
+           for g, a in zip(gs, tmp.state_auxiliary)]
+    run_case("baroclinic_wave_hyperdiffusion", model, gs, Q0s, "rusanov", 0.5, 2, rank, world, False, "horizontal")
     run_ocean(rank, world)
     dist.destroy_process_group()
 

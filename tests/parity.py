@@ -59,8 +59,11 @@ def device_model(om):
                 {"gravity": P.Gravity, "coriolis": P.Coriolis, "held_suarez": P.HeldSuarezForcing}[s]()
                 for s in om.sources)
     bcs = tuple(P.AtmosBC(P.Impenetrable(P.FreeSlip() if b == "freeslip" else P.NoSlip())) for b in om.bcs)
+    hyp = None
+    if getattr(om, "hyperdiffusion", None) is not None:
+        hyp = P.DryBiharmonic(float(om.hyperdiffusion[1]))
     return P.AtmosModel(orientation=orient, ref_state=ref, turbulence=turb, source=src,
-                        boundaryconditions=bcs)
+                        boundaryconditions=bcs, hyperdiffusion=hyp)
 
 
 def make_device_dg(odgm, g, nf, diffusion_direction="every", skip_zero_viscosity=False):
@@ -186,7 +189,7 @@ def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity):
 
 
 def gcm_setup(ne=3, nvert=2, FT=np.float64, turbulence=("constant_kinematic", 0.0, False),
-              csize=1, domain_height=30e3):
+              csize=1, domain_height=30e3, hyperdiffusion=None):
     """Dry baroclinic wave on the cubed sphere (experiments/TestCase/baroclinic_wave.jl with
     explicit stepping, no hyperdiffusion): spherical orientation, hydrostatic reference state
     (DecayingTemperatureProfile 290/220/8 km), Gravity + Coriolis, free-slip walls."""
@@ -198,7 +201,8 @@ def gcm_setup(ne=3, nvert=2, FT=np.float64, turbulence=("constant_kinematic", 0.
     model = oatmos.DryAtmosModel(
         FT, orientation="spherical",
         ref_state=dict(T_surf=290.0, T_min=220.0, H_t=8e3, subtract_off=True),
-        turbulence=turbulence, sources=("gravity", "coriolis"), bcs=("freeslip", "freeslip"))
+        turbulence=turbulence, sources=("gravity", "coriolis"), bcs=("freeslip", "freeslip"),
+        hyperdiffusion=hyperdiffusion)
     return model, gs
 
 
@@ -312,18 +316,20 @@ def courant_case():
 
 
 def box_setup(nelem=(3, 2, 3), FT=np.float64, turbulence=("smagorinsky", 0.21), csize=1,
-              periodic_z=False):
+              periodic_z=False, hyperdiffusion=None, periodic_xy=(True, True)):
     """LES-like box (tutorials/Atmos/risingbubble.jl without tracers): flat orientation,
     hydrostatic reference state, gravity, walls top/bottom, periodic horizontally."""
     br = (np.linspace(0, 1500, nelem[0] + 1), np.linspace(0, 1000, nelem[1] + 1),
           np.linspace(0, 1500, nelem[2] + 1))
-    topos = tp.StackedBrickTopology(csize, br, periodicity=(True, True, periodic_z),
-                                    boundary=((0, 0), (0, 0), (1, 2)))
+    topos = tp.StackedBrickTopology(csize, br, periodicity=(periodic_xy[0], periodic_xy[1], periodic_z),
+                                    boundary=((0, 0) if periodic_xy[0] else (1, 2),
+                                              (0, 0) if periodic_xy[1] else (2, 1), (1, 2)))
     gs = [ogrids.Grid(t, 4, FT=FT) for t in topos]
     model = oatmos.DryAtmosModel(
         FT, orientation="flat",
         ref_state=dict(T_surf=300.0, T_min=220.0, H_t=8e3, subtract_off=True),
-        turbulence=turbulence, sources=("gravity",), bcs=("freeslip", "noslip"))
+        turbulence=turbulence, sources=("gravity",), bcs=("freeslip", "noslip"),
+        hyperdiffusion=hyperdiffusion)
     return model, gs
 
 
@@ -353,6 +359,54 @@ def box_case(nf="rusanov", nsteps=1, dt=0.01, turbulence=("smagorinsky", 0.21),
     Q0 = bubble_state(model, g, aux)
     return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
                         diffusion_direction=diffusion_direction)
+
+
+def hyperdiffusion_case(kind="sphere", nsteps=2, turbulence=("constant_kinematic", 0.0, False),
+                        tau=None, nf="rusanov"):
+    """DryBiharmonic(tau) with diffusion_direction = HorizontalDirection(), as the GCM
+    drivers configure it (experiments/TestCase/baroclinic_wave.jl:179, AtmosGCM/heldsuarez.jl:195).
+    kind: "sphere" (cubed sphere, panel flips), "box" (flat box, periodic horizontally), "walled_box"
+    (horizontal walls: the no-op boundary states of the divergence / higher-order fluxes).
+    Besides the usual differences returns the hyperdiffusion's own share of the oracle tendency and
+    the device-vs-oracle difference of that share alone."""
+    # 8 h on the sphere as the drivers set it; 30 s on the 1.5 km box so that the term is of comparable
+    # relative size there
+    hyp = ("dry_biharmonic", tau or (8 * 3600.0 if kind == "sphere" else 30.0))
+    if kind == "sphere":
+        model, gs = gcm_setup(3, 2, turbulence=turbulence, hyperdiffusion=hyp)
+        model0, _ = gcm_setup(3, 2, turbulence=turbulence)
+        dt = 0.5
+    else:
+        pxy = (True, True) if kind == "box" else (False, False)
+        model, gs = box_setup((3, 2, 3), turbulence=turbulence, hyperdiffusion=hyp, periodic_xy=pxy)
+        model0, _ = box_setup((3, 2, 3), turbulence=turbulence, periodic_xy=pxy)
+        dt = 0.01
+    g = gs[0]
+    odgm = odg.DGModel(model, [g], nf, diffusion_direction="horizontal")
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_baroclinic_wave(model, aux) if kind == "sphere" else bubble_state(model, g, aux)
+    res = compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt, diffusion_direction="horizontal")
+    # the hyperdiffusion's own contribution: tendency(with) - tendency(without), oracle and device
+    P = pkg()
+    tend = {}
+    for name, mm in (("with", model), ("without", model0)):
+        o = odg.DGModel(mm, [g], nf, diffusion_direction="horizontal")
+        q = omsa.MPIStateArray.from_grid(g, 5)
+        np.moveaxis(q.data[:g.nreal], 1, 0)[...] = Q0
+        omsa.ghost_exchange([q])
+        dq = q.similar()
+        o([dq], [q], 0.0, 1, 0)
+        dg, dgrid = make_device_dg(o, g, nf, "horizontal")
+        dQ = P.MPIStateArray(dgrid, 5, data=q.data)
+        dT = P.MPIStateArray(dgrid, 5)
+        dg(dT, dQ, None, 0.0, 1.0, 0.0)
+        tend[name] = (dq.realdata.copy(), dT.realdata.cpu().numpy())
+        dg.close()
+    osh = tend["with"][0] - tend["without"][0]
+    dsh = tend["with"][1] - tend["without"][1]
+    res["hyper_share_of_tendency"] = rel_l2(tend["with"][0], tend["without"][0])
+    res["hyper_share_rel_l2"] = rel_l2(dsh, osh)
+    return res
 
 
 # ---------------------------------------------------------------------------------------

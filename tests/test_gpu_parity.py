@@ -110,6 +110,28 @@ def test_held_suarez_forcing_and_sponge(turbulence):
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+@pytest.mark.parametrize("kind,turbulence", [
+    ("sphere", ("constant_kinematic", 0.0, False)),      # baroclinic_wave.jl as shipped
+    ("sphere", ("smagorinsky", 0.21)),                   # heldsuarez.jl closures
+    ("box", ("constant_kinematic", 75.0, False)),
+    ("walled_box", ("smagorinsky", 0.21)),
+])
+def test_dry_biharmonic_hyperdiffusion(kind, turbulence):
+    """DryBiharmonic hyperdiffusion passes (three kernels: gradient with u_h / h_tot,
+    divergence of gradients, gradient of Laplacians + total diffusive flux), horizontal direction.
+    Parity unpinned in the reference (convergence tests of another balance law only): oracle = the
+    restatement, checked analytically in tests/test_oracle_hyperdiffusion.py."""
+    res = parity.hyperdiffusion_case(kind=kind, turbulence=turbulence, nsteps=2)
+    assert res["gradflux_rel_l2"] <= 1e-12, res
+    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
+    assert res["tendency_inc_rel_l2"] <= TOL_TEND_F64, res
+    assert res["state_rel_l2"] <= 1e-12, res
+    assert res["state_unfused_rel_l2"] <= 1e-12, res
+    # the hyperdiffusive part is visible in the tendency and agrees on its own
+    assert res["hyper_share_of_tendency"] > 1e-8, res
+    assert res["hyper_share_rel_l2"] <= 1e-6, res
+
+
 @pytest.mark.parametrize("direction", ["every", "horizontal", "vertical"])
 @pytest.mark.parametrize("target", ["indices", "atmos_perturbations"])
 def test_filters_apply(direction, target):
@@ -151,7 +173,7 @@ def test_multi_gpu_halo_and_parity():
          os.path.join(root, "tests", "multi_gpu_parity.py")],
         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MULTI_GPU_PARITY") == 4
+    assert out.stdout.count("MULTI_GPU_PARITY") == 5
 
 
 def test_ocean_hbmodel_tendency_and_steps():
