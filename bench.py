@@ -124,7 +124,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # libcmdg arm
 # ----------------------------------------------------------------------------------------
-def build_case(P, workload, ne, nvert, rank, nranks, device):
+def build_case(P, workload, ne, nvert, rank, nranks, device, hyper=False):
     import numpy as np
     import torch
     from climatemachine_jl_b200 import topologies as tp, grids as gr, atmos_init as ai
@@ -142,7 +142,8 @@ def build_case(P, workload, ne, nvert, rank, nranks, device):
                                  turbulence=P.SmagorinskyLilly(0.21),
                                  source=(P.Gravity(), P.Coriolis(), P.HeldSuarezForcing(),
                                          P.RayleighSponge(30e3, 12e3, 1 / 60 / 15, (0.0, 0.0, 0.0), 2.0)),
-                                 boundaryconditions=(P.AtmosBC(), P.AtmosBC()))
+                                 boundaryconditions=(P.AtmosBC(), P.AtmosBC()),
+                                 hyperdiffusion=P.DryBiharmonic(8 * 3600.0) if hyper else None)
             aux = P.MPIStateArray(grid, model.number_states("Auxiliary"))
             dg = P.DGModel(model, grid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
                            P.CentralNumericalFluxGradient(), state_auxiliary=aux,
@@ -152,8 +153,17 @@ def build_case(P, workload, ne, nvert, rank, nranks, device):
                              ref_state=P.HydrostaticState(P.DecayingTemperatureProfile(290.0, 220.0, 8e3)),
                              turbulence=P.ConstantKinematicViscosity(0.0),
                              source=(P.Gravity(), P.Coriolis()),
-                             boundaryconditions=(P.AtmosBC(), P.AtmosBC()))
+                             boundaryconditions=(P.AtmosBC(), P.AtmosBC()),
+                             hyperdiffusion=P.DryBiharmonic(8 * 3600.0) if hyper else None)
         dt = 0.4     # s; vertical acoustic CFL ~0.3
+        if hyper:
+            # experiments/TestCase/baroclinic_wave.jl:179,258 as shipped: DryBiharmonic(8 h) with the
+            # horizontal diffusion direction; the nu = 0 gradient pass cannot be skipped then
+            aux = P.MPIStateArray(grid, model.number_states("Auxiliary"))
+            dg = P.DGModel(model, grid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                           P.CentralNumericalFluxGradient(), state_auxiliary=aux,
+                           diffusion_direction=P.HorizontalDirection(), write_aux_diagnostics=True)
+            return dict(topo=topo, grid=grid, model=model, dg=dg, aux=aux, dt=dt, ai=ai)
     elif workload == "ocean_gyre":
         # BASELINE.json configs[4]: OceanBoxGCM HBModel, 20 x 20 x 50 elements per GPU
         # (experiments/OceanBoxGCM/homogeneous_box.jl:11-21), box widened in x with the GPU count
@@ -206,7 +216,7 @@ def run_b200(args):
         ne = args.ne or (WEAK_NE.get(world, int(round(32 * world ** 0.5)))
                          if args.workload in ("baroclinic_wave", "held_suarez")
                          else int(round(64 * world ** (1 / 3))))
-    case = build_case(P, args.workload, ne, args.nvert, rank, world, dev)
+    case = build_case(P, args.workload, ne, args.nvert, rank, world, dev, hyper=args.hyperdiffusion)
     dg, grid, model, ai = case["dg"], case["grid"], case["model"], case["ai"]
     if world > 1:
         uid = [P.comm_unique_id() if rank == 0 else None]
@@ -337,15 +347,17 @@ def run_b200(args):
                                 "Rusanov, LSRK54, dt=0.4 s" if args.workload == "baroclinic_wave"
                                 else f"Held-Suarez dry GCM + SmagorinskyLilly(0.21) (gradient pass + viscous fluxes, horizontal "
                                 f"diffusion direction), sources Gravity/Coriolis/HeldSuarezForcing/RayleighSponge, cubed sphere "
-                                f"ne={ne} x {args.nvert}, N=4, Rusanov, LSRK54, dt=0.4 s, hyperdiffusion off"
+                                f"ne={ne} x {args.nvert}, N=4, Rusanov, LSRK54, dt=0.4 s"
                                 if args.workload == "held_suarez"
                                 else f"OceanBoxGCM HBModel ocean gyre, {ne * world}x{ne}x{args.nvert} elements, N=4, "
                                 "Rusanov, LSRK144 (a step = 14 stages), dt=55 s" if ocean
                                 else f"isentropic vortex, periodic box {ne}^3, N=4, Rusanov, LSRK54"),
+                   "hyperdiffusion": ("DryBiharmonic(8 h), horizontal (3 extra kernels + 2 extra exchanges per evaluation)"
+                                      if args.hyperdiffusion else "off"),
                    "nelem_total": int(nodes / NP), "dof_total": int(dof),
                    "cache": "inputs larger than L2 (Q+dQ+Qout+aux+geometry = %.0f MB per GPU vs 126 MB L2)"
                             % (nodes_local * 8 * (3 * NSTATE + case["aux"].nstate + 10 + 4.8 + (10 if ocean else 0)) / 1e6),
-                   "skip_zero_viscosity": not ocean and args.workload != "held_suarez", "parallelism": f"element partition x{world}"},
+                   "skip_zero_viscosity": not ocean and args.workload != "held_suarez" and not args.hyperdiffusion, "parallelism": f"element partition x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "hb_tendency_kernel<double,5,RUSANOV>" if ocean else "dg_tendency_kernel<double,5,RUSANOV,...>",
@@ -360,7 +372,8 @@ def run_b200(args):
         "clocks": clk,
         "norm_ratio": norm1 / norm0,
     }
-    if world == 1 and not args.no_cpu_baseline and not ocean and args.workload != "held_suarez":
+    if world == 1 and not args.no_cpu_baseline and not ocean and args.workload != "held_suarez" \
+            and not args.hyperdiffusion:
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -466,6 +479,8 @@ def main():
     ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex", "ocean_gyre", "held_suarez"])
     ap.add_argument("--ne", type=int, default=0, help="horizontal elements per cube edge / box edge")
     ap.add_argument("--nvert", type=int, default=10)
+    ap.add_argument("--hyperdiffusion", action="store_true",
+                    help="baroclinic_wave / held_suarez as the reference's drivers ship them: DryBiharmonic(8 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -70,7 +70,7 @@ SYMBOLS = [
     "cmdg_bind_state", "cmdg_tendency", "cmdg_lsrk_update", "cmdg_lsrk_steps",
     "cmdg_lsrk_steps_host", "cmdg_comm_unique_id", "cmdg_comm_init", "cmdg_exchange_begin",
     "cmdg_exchange_end", "cmdg_sync", "cmdg_kernel_launches", "cmdg_set_timing",
-    "cmdg_last_kernel_ms", "cmdg_set_ocean_model", "cmdg_bind_ocean_operators",
+    "cmdg_last_kernel_ms", "cmdg_kernel_class_ms", "cmdg_set_ocean_model", "cmdg_bind_ocean_operators",
     "cmdg_filter_apply", "cmdg_set_step_filter", "cmdg_courant",
 ]
 
@@ -115,6 +115,8 @@ def lib():
     L.cmdg_set_timing.argtypes = [vp, i32]
     L.cmdg_last_kernel_ms.argtypes = [vp, C.POINTER(i64)]
     L.cmdg_last_kernel_ms.restype = dbl
+    L.cmdg_kernel_class_ms.argtypes = [vp, i32, C.POINTER(i64)]
+    L.cmdg_kernel_class_ms.restype = dbl
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("cmdg_version",):

@@ -123,6 +123,10 @@ struct cmdg_handle_s {
   size_t tev_used = 0;
   double last_ms = -1;
   int64_t last_nl = 0;
+  // kernel class of every timed launch (CMDG_KCLASS_*) and the per-class totals of the last call
+  std::vector<int> tev_class;
+  double class_ms[CMDG_KCLASS_COUNT] = {0};
+  int64_t class_n[CMDG_KCLASS_COUNT] = {0};
 };
 
 namespace {
@@ -205,12 +209,14 @@ int expected_naux(const cmdg_desc &d) {
   return c + 2;
 }
 
-cudaEvent_t timing_event(cmdg_handle h) {
+cudaEvent_t timing_event(cmdg_handle h, int kclass = CMDG_KCLASS_TENDENCY) {
   if (h->tev_used == h->tev.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     h->tev.push_back(e);
+    h->tev_class.push_back(0);
   }
+  h->tev_class[h->tev_used] = kclass;
   return h->tev[h->tev_used++];
 }
 
@@ -287,7 +293,9 @@ int launch_gradient_inst(cmdg_handle h, const GradArgs<R> &a, const AtmosParams<
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
     attr_set = true;
   }
+  if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
   kern<<<(unsigned)n, Dims<5>::BLOCK, sizeof(SM), st>>>(a, P);
+  if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
   CU(cudaGetLastError());
   h->launches++;
   return 0;
@@ -320,18 +328,22 @@ HyperArgs<R> hyper_args(cmdg_handle h, const void *Q) {
   a.Qhd = (R *)h->Qhd;
   a.F2 = (R *)h->F2dev;
   a.Fn = (R *)h->FnDev;
+  a.pf_dist = h->pf_dist;
   return a;
 }
 template <class R>
 int launch_hyper(cmdg_handle h, int pass, const HyperArgs<R> &a, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   if (int rc = ensure_const_D<R>(h, st)) return rc;
+  const int kc = pass == 2 ? CMDG_KCLASS_HYPER_DIVERGENCE : CMDG_KCLASS_HYPER_FLUX;
+  if (h->timing) cudaEventRecord(timing_event(h, kc), st);
   if (pass == 2) {
     hyper_divergence_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a);
   } else {
     const AtmosParams<R> P = make_params<R>(h);
     hyper_flux_kernel<R, 5, true><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
   }
+  if (h->timing) cudaEventRecord(timing_event(h, kc), st);
   CU(cudaGetLastError());
   h->launches++;
   return 0;
@@ -602,7 +614,7 @@ int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double 
   a.t = (R)t;
   GradArgs<R> ga{(const R *)Q, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
                  (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev,
-                 (R *)h->Qhg};
+                 (R *)h->Qhg, h->pf_dist};
   int rc;
   if (!par) {
     if (h->visc && (rc = second_order_passes<R>(h, ga, Q, false, false, false, st))) return rc;
@@ -714,7 +726,12 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       if (s != nstage - 1) a.aux_out = nullptr;
       GradArgs<R> ga{cur, (const R *)h->aux, (R *)h->gradflux, (const R *)h->vgeoP,
                      (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev,
-                     (R *)h->Qhg};
+                     (R *)h->Qhg, h->pf_dist};
+      // like the aux diagnostics, state_gradient_flux is only read after the step: the last stage
+      // refreshes it (the tendency kernel consumes F2 / Fn, not GF); DryBiharmonic with a non-zero
+      // viscous closure re-reads GF in hyper_flux_kernel, so it is kept then
+      const bool gf_needed = h->hyper && (h->d.turbulence == CMDG_TURB_SMAGORINSKY || h->d.turb_param != 0.0);
+      if (s != nstage - 1 && !gf_needed) ga.gradflux = nullptr;
       int rc;
       if (!par) {
         if (h->visc && (rc = second_order_passes<R>(h, ga, cur, false, true, false, st))) return rc;
@@ -759,13 +776,18 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   if (h->timing) {
     CU(cudaStreamSynchronize(st));
     double ms = 0;
+    int64_t nl = 0;
+    for (int c = 0; c < CMDG_KCLASS_COUNT; ++c) h->class_ms[c] = 0, h->class_n[c] = 0;
     for (size_t i = 0; i + 1 < h->tev_used; i += 2) {
       float x = 0;
       cudaEventElapsedTime(&x, h->tev[i], h->tev[i + 1]);
-      ms += x;
+      const int c = h->tev_class[i];
+      h->class_ms[c] += x;
+      h->class_n[c]++;
+      if (c == CMDG_KCLASS_TENDENCY) ms += x, nl++;
     }
     h->last_ms = ms;
-    h->last_nl = (int64_t)(h->tev_used / 2);
+    h->last_nl = nl;
   }
   return 0;
 }
@@ -1354,6 +1376,12 @@ double cmdg_last_kernel_ms(cmdg_handle h, int64_t *nl) {
   if (!h) return -1;
   if (nl) *nl = h->last_nl;
   return h->last_ms;
+}
+
+double cmdg_kernel_class_ms(cmdg_handle h, int32_t kclass, int64_t *nl) {
+  if (!h || kclass < 0 || kclass >= CMDG_KCLASS_COUNT || h->last_ms < 0) return -1;
+  if (nl) *nl = h->class_n[kclass];
+  return h->class_ms[kclass];
 }
 
 }  // extern "C"

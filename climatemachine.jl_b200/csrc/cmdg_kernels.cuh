@@ -1017,6 +1017,7 @@ struct GradArgs {
   R *Fn;   // [nreal][6*Nfp][4]
   // DryBiharmonic (HYPER kernels): gradient of (u_h, h_tot), column 3*s + d  [nelem][12][Np]
   R *Qhg;
+  int pf_dist;   // L2 prefetch distance in launch-list entries (0 = off)
 };
 
 template <class R>
@@ -1060,31 +1061,60 @@ __device__ __forceinline__ void gradient_flux(const AtmosParams<R> &P, const R d
 // (volume + central face term, DGModel_kernels.jl:1081-1098, 1618-1628) go to Qhg.  grad h_tot is
 // the first three gradient-flux columns, so only u_h costs extra contractions.  The diffusive flux is
 // then assembled by hyper_flux_kernel, not here.
+// Fn[e][it][0..3] = n . F2[.][1..4] at the <= 3 face nodes that coincide with volume node (i, j, k)
+template <class R, int NQ>
+__device__ __forceinline__ void write_normal_flux(const R *__restrict__ sgeoP, R *__restrict__ Fn, int e,
+                                                  int i, int j, int k, const R F2[3][5]) {
+  constexpr int NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
+  typedef typename Vec2<R>::type V2;
+  const int fit[3] = {(i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1),
+                      (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1),
+                      (k == 0) ? 4 * NFP + i + NQ * j : ((k == NQ - 1) ? 5 * NFP + i + NQ * j : -1)};
+#pragma unroll
+  for (int dir = 0; dir < 3; ++dir) {
+    const int it = fit[dir];
+    if (it < 0) continue;
+    R n[3], sMvMI;
+    load_sgeo<R>(sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
+    V2 o0, o1;
+    o0.x = n[0] * F2[0][1] + n[1] * F2[1][1] + n[2] * F2[2][1];
+    o0.y = n[0] * F2[0][2] + n[1] * F2[1][2] + n[2] * F2[2][2];
+    o1.x = n[0] * F2[0][3] + n[1] * F2[1][3] + n[2] * F2[2][3];
+    o1.y = n[0] * F2[0][4] + n[1] * F2[1][4] + n[2] * F2[2][4];
+    V2 *po = reinterpret_cast<V2 *>(Fn + ((size_t)e * NFN + it) * 4);
+    po[0] = o0;
+    po[1] = o1;
+  }
+}
+
+// The face term is linear in (G* - G-), so a face item only stores w = vMI sM (G* - G-) (5 values, in
+// place of the neighbour trace it consumed); the node thread accumulates n (x) w of its <= 3 faces
+// onto its volume gradient and applies the gradient-flux map ONCE -- half the shared-memory traffic
+// of storing / re-reading 10 flux columns per face node (the kernel is LSU-bound like the tendency
+// kernel).  n . F2 at the element's own face nodes is written by the node threads too (no staging).
 template <class R, int NQ, bool AUX, bool HYPER>
 struct GradSmem {
   static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
-  R G[5][NP];
-  R Q[5][NP];
+  R G[5][NP];                         // gradient arguments at my nodes
+  R Q[5][NP];                         // my state (wall boundary states only)
   R Phi[AUX ? NP : 1];
-  R Face[10][NFN];
-  R Qp[6][NFN];                       // neighbour traces (Q+, Phi+), gathered asynchronously
+  R Qp[6][NFN];                       // neighbour traces (Q+, Phi+), gathered asynchronously; then w
   R Uh[HYPER ? 3 : 1][HYPER ? NP : 1];     // u_h at my nodes
   R K[HYPER ? 3 : 1][HYPER ? NP : 1];      // k = grad Phi / grav at my nodes
-  R Kp[HYPER ? 3 : 1][HYPER ? NFN : 1];    // neighbour grad Phi
-  R FaceH[HYPER ? 9 : 1][HYPER ? NFN : 1]; // face terms of grad u_h
+  R Kp[HYPER ? 3 : 1][HYPER ? NFN : 1];    // neighbour grad Phi; then w of u_h
 };
 
 template <class R, int NQ, bool AUX, bool HYPER>
-__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (HYPER ? 3 : CMDG_GRAD_MINBLOCKS) : 1))
+__global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? (HYPER ? 4 : CMDG_GRAD_MINBLOCKS) : 1))
 dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK;
+  typedef typename Vec2<R>::type V2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GradSmem<R, NQ, AUX, HYPER> &S = *reinterpret_cast<GradSmem<R, NQ, AUX, HYPER> *>(smem_raw);
   R(&sG)[5][NP] = S.G;
   R(&sQ)[5][NP] = S.Q;
   R(&sPhi)[AUX ? NP : 1] = S.Phi;
-  R(&sFace)[10][NFN] = S.Face;
   R(&sQp)[6][NFN] = S.Qp;
   constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
   const int tid = threadIdx.x;
@@ -1092,6 +1122,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   const size_t eoffQ = (size_t)e * 5 * NP;
   const size_t eoffA = (size_t)e * P.naux * NP;
   const int nfaces = P.horizontal_diffusion ? 4 : 6;
+  const bool smag = P.turbulence == TURB_SMAGORINSKY;
   // face descriptors of my items, then cp.async gathers of the neighbour state: their latency
   // overlaps the node phase (the same thread consumes what it gathered: no barrier needed)
   int2 cn[NITEM];
@@ -1099,6 +1130,22 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   for (int r = 0; r < NITEM; ++r) {
     const int it = tid + r * BLOCK;
     cn[r] = (it < nfaces * NFP) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 16);
+    if (it < NFN) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.sgeoP + ((size_t)e * NFN + it) * 4));
+  }
+  // L2 prefetch for the block that will replace this one on the SM (see dg_tendency_kernel)
+  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
+    const int bn = blockIdx.x + A.pf_dist;
+    const int en = A.elems ? A.elems[bn] : bn;
+    prefetch_l2_bulk(A.Q + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
+    prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
+    if (AUX && P.a_Phi >= 0) {
+      // Phi, and grad Phi (the three columns after it) when the closure / u_h projection needs it
+      const int ncol = (HYPER || smag) ? 4 : 1;
+      prefetch_l2_bulk(A.aux + ((size_t)en * P.naux + P.a_Phi) * NP, (size_t)ncol * NP * sizeof(R));
+      if (P.a_Delta >= 0) prefetch_l2_bulk(A.aux + ((size_t)en * P.naux + P.a_Delta) * NP, NP * sizeof(R));
+    }
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
   }
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
@@ -1124,16 +1171,19 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
     }
   }
 
-  R q[5] = {1, 0, 0, 0, 0}, G[5], Phi = 0, gPhi[3] = {0, 0, 0};
+  R q[5] = {1, 0, 0, 0, 0}, G[5], Phi = 0, gPhi[3] = {0, 0, 0}, Delta = 0;
+  R g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, MI = 0;
   const R inv_grav = R(1) / P.grav;
   if (tid < NP) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = A.Q[eoffQ + (size_t)s * NP + tid];
     if (AUX && P.a_Phi >= 0) Phi = A.aux[eoffA + (size_t)P.a_Phi * NP + tid];
-    if (AUX && P.a_gradPhi >= 0 && (HYPER || P.turbulence == TURB_SMAGORINSKY)) {
+    if (AUX && P.a_gradPhi >= 0 && (HYPER || smag)) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
     }
+    if (!HYPER && AUX && P.a_Delta >= 0 && A.F2) Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
+    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
     gradient_argument<R>(P, q, Phi, G);
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
@@ -1153,7 +1203,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   }
   __syncthreads();
 
-  // faces: vMI sM gf(n (x) (G* - G-)),  G* = (G+ + G-)/2 or g(boundary_state(Q-))
+  // faces: w = vMI sM (G* - G-),  G* = (G+ + G-)/2 or g(boundary_state(Q-))
   cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
@@ -1163,20 +1213,12 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
     const int2 c = cn[r];
     const int bctag = (c.y >> 4) & 15;
     const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
-    R n[3], sMvMI;
-    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
-    R Gm[5], qm[5], qp[5], Gs[5];
+    const V2 *pg = reinterpret_cast<const V2 *>(A.sgeoP + ((size_t)e * NFN + it) * 4);
+    const V2 g1 = pg[1];            // n3, sM vMI
+    const R sMvMI = g1.y;
+    R Gm[5], qp[5], Gs[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      Gm[s] = sG[s][vm];
-      qm[s] = sQ[s][vm];
-    }
-    const R Phim = AUX ? sPhi[AUX ? vm : 0] : R(0);
-    R gPm[3] = {0, 0, 0};
-    if (P.turbulence == TURB_SMAGORINSKY) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) gPm[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + vm];
-    }
+    for (int s = 0; s < 5; ++s) Gm[s] = sG[s][vm];
     R uhm[3] = {0, 0, 0}, dUh[3] = {0, 0, 0};
     if (HYPER) {
 #pragma unroll
@@ -1199,11 +1241,14 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int s = 0; s < 5; ++s) Gs[s] = R(0.5) * (Gs[s] + Gm[s]) - Gm[s];
     } else {
       // gradient-flux boundary state (bc_momentum.jl:34-43, 71-80)
+      const V2 g0 = pg[0];
+      const R n[3] = {g0.x, g0.y, g1.x};
 #pragma unroll
-      for (int s = 0; s < 5; ++s) qp[s] = qm[s];
+      for (int s = 0; s < 5; ++s) qp[s] = sQ[s][vm];
+      const R Phim = AUX ? sPhi[AUX ? vm : 0] : R(0);
       const int kind = P.bc_kind[bctag - 1];
       if (kind == BC_FREESLIP) {
-        const R run = qm[1] * n[0] + qm[2] * n[1] + qm[3] * n[2];
+        const R run = qp[1] * n[0] + qp[2] * n[1] + qp[3] * n[2];
         qp[1] -= run * n[0];
         qp[2] -= run * n[1];
         qp[3] -= run * n[2];
@@ -1221,30 +1266,21 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) Gs[s] -= Gm[s];
     }
+    // in place of the trace this thread gathered (nobody else touches the slot)
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+      if (s < 4 || smag) sQp[s][it] = sMvMI * Gs[s];
     if (HYPER) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) S.FaceH[HYPER ? 3 * c + d : 0][HYPER ? it : 0] = sMvMI * (n[d] * dUh[c]);
+      for (int d = 0; d < 3; ++d) S.Kp[HYPER ? d : 0][HYPER ? it : 0] = sMvMI * dUh[d];
     }
-    R dG[3][5];
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-      for (int s = 0; s < 5; ++s) dG[d][s] = n[d] * Gs[s];
-    R gf[10];
-    gradient_flux<R>(P, dG, gPm, Gm[4], gf);
-#pragma unroll
-    for (int s = 0; s < 10; ++s) sFace[s][it] = sMvMI * gf[s];
   }
 
   // volume: strong-form gradient  xi_x * (D G)
-  R gfv[10];
-  R hgv[HYPER ? 9 : 1];
+  R dG[3][5];
+  R dH[HYPER ? 3 : 1][3];   // dH[d][c] = d u_h,c / d x_d
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   if (tid < NP) {
-    R g[9], MI;
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
 #pragma unroll
     for (int c = 0; c < 9; ++c) g[c] *= MI;  // packed copy holds M*xi_x
     R G1[5] = {0, 0, 0, 0, 0}, G2[5] = {0, 0, 0, 0, 0}, G3[5] = {0, 0, 0, 0, 0};
@@ -1254,19 +1290,18 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       const int o1 = n + NQ * (j + NQ * k), o2 = i + NQ * (n + NQ * k), o3 = i + NQ * (j + NQ * n);
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
+        if (s == 4 && !smag) continue;
         G1[s] += d1 * sG[s][o1];
         G2[s] += d2 * sG[s][o2];
-        G3[s] += d3 * sG[s][o3];
+        if (!P.horizontal_diffusion) G3[s] += d3 * sG[s][o3];
       }
     }
-    R dG[3][5];
     const R vfac = P.horizontal_diffusion ? R(0) : R(1);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
       for (int s = 0; s < 5; ++s)
         dG[d][s] = g[d] * G1[s] + g[3 + d] * G2[s] + vfac * (g[6 + d] * G3[s]);
-    gradient_flux<R>(P, dG, gPhi, G[4], gfv);
     if (HYPER) {
       // horizontal gradient of u_h (the diffusion direction is horizontal with DryBiharmonic)
       R H1[3] = {0, 0, 0}, H2[3] = {0, 0, 0};
@@ -1283,79 +1318,70 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) hgv[3 * c + d] = g[d] * H1[c] + g[3 + d] * H2[c];
+        for (int d = 0; d < 3; ++d) dH[HYPER ? d : 0][c] = g[d] * H1[c] + g[3 + d] * H2[c];
     }
   }
   __syncthreads();
-  if (tid < NP) {
-    const bool vert = !P.horizontal_diffusion;
-    if (i == 0)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][0 * NFP + j + NQ * k];
-    if (i == NQ - 1)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][1 * NFP + j + NQ * k];
-    if (j == 0)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][2 * NFP + i + NQ * k];
-    if (j == NQ - 1)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][3 * NFP + i + NQ * k];
-    if (vert && k == 0)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][4 * NFP + i + NQ * j];
-    if (vert && k == NQ - 1)
-      for (int s = 0; s < 10; ++s) gfv[s] += sFace[s][5 * NFP + i + NQ * j];
-    const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
-    for (int s = 0; s < P.ngradflux; ++s) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
-    if (HYPER) {
-      const int fi[2] = {(i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1),
-                         (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1)};
+  if (tid >= NP) return;
+  // my <= 3 faces: item index per direction (-1 = interior node in that direction)
+  const int fit[3] = {(i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1),
+                      (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1),
+                      P.horizontal_diffusion ? -1
+                                             : ((k == 0) ? 4 * NFP + i + NQ * j
+                                                         : ((k == NQ - 1) ? 5 * NFP + i + NQ * j : -1))};
 #pragma unroll
-      for (int f2 = 0; f2 < 2; ++f2)
-        if (fi[f2] >= 0) {
-#pragma unroll
-          for (int c = 0; c < 9; ++c) hgv[c] += S.FaceH[HYPER ? c : 0][HYPER ? fi[f2] : 0];
-        }
-      const size_t eoffH = (size_t)e * 12 * NP + tid;
-#pragma unroll
-      for (int c = 0; c < 9; ++c) A.Qhg[eoffH + (size_t)c * NP] = hgv[c];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) A.Qhg[eoffH + (size_t)(9 + d) * NP] = gfv[d];
-    }
-  }
-  if (HYPER || !A.F2) return;
-  // ---- second-order flux F2(Q, GF, aux) of this node, once (flux_second_order!, kernels.jl:84-105):
-  // the tendency kernel then needs no closure evaluation, neither in the volume nor on faces.
-  // F2 goes to global memory (volume term, ghost exchange) and, through shared memory, into
-  // n . F2 at the element's 6 * Nfp own face nodes.
-  __syncthreads();                       // sFace has been consumed
-  R(*sF2)[NP] = reinterpret_cast<R(*)[NP]>(&sFace[0][0]);   // 12 * Np <= 10 * 6 * Nfp doubles
-  static_assert(12 * NP <= 10 * NFN, "F2 staging reuses the face buffer");
-  if (tid < NP) {
-    R Delta = R(0);
-    if (AUX && P.a_Delta >= 0) Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
-    R F2[3][5];
-    flux_second_order<R>(P, q, gfv, gPhi, Delta, F2);
-    const size_t eoffF = (size_t)e * 12 * NP + tid;
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-      for (int c = 1; c < 5; ++c) {
-        A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
-        sF2[4 * d + c - 1][tid] = F2[d][c];
-      }
-  }
-  __syncthreads();
-  for (int it = tid; it < NFN; it += BLOCK) {
-    const int f = it / NFP, fn = it - f * NFP;
-    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+  for (int dir = 0; dir < 3; ++dir) {
+    const int it = fit[dir];
+    if (it < 0) continue;
     R n[3], sMvMI;
     load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
-    typename Vec2<R>::type o0, o1;
-    o0.x = n[0] * sF2[0][vm] + n[1] * sF2[4][vm] + n[2] * sF2[8][vm];
-    o0.y = n[0] * sF2[1][vm] + n[1] * sF2[5][vm] + n[2] * sF2[9][vm];
-    o1.x = n[0] * sF2[2][vm] + n[1] * sF2[6][vm] + n[2] * sF2[10][vm];
-    o1.y = n[0] * sF2[3][vm] + n[1] * sF2[7][vm] + n[2] * sF2[11][vm];
-    typename Vec2<R>::type *po = reinterpret_cast<typename Vec2<R>::type *>(A.Fn + ((size_t)e * NFN + it) * 4);
-    po[0] = o0;
-    po[1] = o1;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      if (s == 4 && !smag) continue;
+      const R w = sQp[s][it];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dG[d][s] += n[d] * w;
+    }
+    if (HYPER) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const R w = S.Kp[HYPER ? c : 0][HYPER ? it : 0];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dH[HYPER ? d : 0][c] += n[d] * w;
+      }
+    }
   }
+  R gfv[10];
+  gradient_flux<R>(P, dG, gPhi, G[4], gfv);
+  if (A.gradflux) {
+    const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+#pragma unroll
+    for (int s = 0; s < 10; ++s)
+      if (s < P.ngradflux) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
+  }
+  if (HYPER) {
+    const size_t eoffH = (size_t)e * 12 * NP + tid;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) A.Qhg[eoffH + (size_t)(3 * c + d) * NP] = dH[HYPER ? d : 0][c];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) A.Qhg[eoffH + (size_t)(9 + d) * NP] = gfv[d];
+    return;
+  }
+  if (!A.F2) return;
+  // ---- second-order flux F2(Q, GF, aux) of this node, once (flux_second_order!, kernels.jl:84-105):
+  // the tendency kernel then needs no closure evaluation, neither in the volume nor on faces.
+  // F2 goes to global memory (volume term, ghost exchange) and, contracted with the face normals of
+  // the <= 3 faces this node lies on, to Fn.
+  R F2[3][5];
+  flux_second_order<R>(P, q, gfv, gPhi, Delta, F2);
+  const size_t eoffF = (size_t)e * 12 * NP + tid;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int c = 1; c < 5; ++c) A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
+  write_normal_flux<R, NQ>(A.sgeoP, A.Fn, e, i, j, k, F2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1380,6 +1406,7 @@ struct HyperArgs {
   R *Qhd;   // [nelem][4][Np]  horizontal Laplacians
   R *F2;    // [nelem][12][Np]
   R *Fn;    // [nreal][6*Nfp][4]
+  int pf_dist;   // L2 prefetch distance in launch-list entries (0 = off)
 };
 
 // Qhd[s] = -MI D^T (M xi_h . grad G_s) + sum_{f<4} vMI sM (grad+ + grad-) . n / 2
@@ -1396,8 +1423,17 @@ hyper_divergence_kernel(const HyperArgs<R> A) {
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   int2 cn = make_int2(0, 16);
+  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
+    const int bn = blockIdx.x + A.pf_dist;
+    const int en = A.elems ? A.elems[bn] : bn;
+    prefetch_l2_bulk(A.Qhg + (size_t)en * 12 * NP, 12 * NP * sizeof(R));
+    prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
+    prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, (size_t)NH * 4 * sizeof(R));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
+  }
   if (tid < NH) {
     cn = A.conn[(size_t)e * 6 + tid / NFP];
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(A.sgeoP + ((size_t)e * NFN + tid) * 4));
     if (((cn.y >> 4) & 15) == 0) {
       const int fn = tid % NFP;
       int a = fn % NQ;
@@ -1485,17 +1521,28 @@ __global__ void __launch_bounds__(Dims<NQ>::BLOCK, (NQ <= 5 ? 4 : 1))
 hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
   constexpr int NP = Dims<NQ>::NP, NFP = Dims<NQ>::NFP, NFN = Dims<NQ>::NFN;
   constexpr int BLOCK = Dims<NQ>::BLOCK, NH = 4 * NFP;
+  typedef typename Vec2<R>::type V2;
   __shared__ R sL[4][NP];
   __shared__ R sNu[NP];
-  __shared__ R sLp[4][NH];
-  __shared__ R sBuf[12 * NP];   // face terms [12][NH] first, then F2 [12][NP]
-  static_assert(12 * NH <= 12 * NP, "face terms fit the F2 staging buffer");
-  R(*sFace)[NH] = reinterpret_cast<R(*)[NH]>(sBuf);
-  R(*sF2)[NP] = reinterpret_cast<R(*)[NP]>(sBuf);
+  __shared__ R sLp[4][NH];      // neighbour Laplacians; then w = vMI sM nu4 (lap+ - lap-) / 2
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
   const size_t eoffA = (size_t)e * P.naux * NP;
   int2 cn = make_int2(0, 16);
+  const bool viscous = P.turbulence == TURB_SMAGORINSKY || P.turb_param != R(0);
+  if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
+    const int bn = blockIdx.x + A.pf_dist;
+    const int en = A.elems ? A.elems[bn] : bn;
+    prefetch_l2_bulk(A.Qhd + (size_t)en * 4 * NP, 4 * NP * sizeof(R));
+    prefetch_l2_bulk(A.Q + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(A.aux + ((size_t)en * P.naux + P.a_Delta_h) * NP, NP * sizeof(R));
+    prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
+    prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
+    if (viscous) prefetch_l2_bulk(A.gradflux + (size_t)en * P.ngradflux * NP, (size_t)P.ngradflux * NP * sizeof(R));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
+  }
+  for (int it = tid; it < NFN; it += BLOCK)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(A.sgeoP + ((size_t)e * NFN + it) * 4));
   if (tid < NH) {
     cn = A.conn[(size_t)e * 6 + tid / NFP];
     if (((cn.y >> 4) & 15) == 0) {
@@ -1510,6 +1557,7 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
     }
   }
   R q[5] = {1, 0, 0, 0, 0}, g[9], MI = 0, nu4 = 0;
+  R gf[10], gPhi[3] = {0, 0, 0}, Delta = R(0);
   if (tid < NP) {
     const size_t eo = (size_t)e * 4 * NP + tid;
 #pragma unroll
@@ -1517,10 +1565,21 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = A.Q[(size_t)e * 5 * NP + (size_t)s * NP + tid];
     const R hD = A.aux[eoffA + (size_t)P.a_Delta_h * NP + tid] * R(0.5);
+    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    if (viscous) {
+      // issued early: consumed after the face terms
+      const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+#pragma unroll
+      for (int s = 0; s < 10; ++s) gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
+      if (AUX && P.turbulence == TURB_SMAGORINSKY) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
+        Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
+      }
+    }
     const R hD2 = hD * hD;
     nu4 = hD2 * hD2 / R(2) / P.hyper_tau;
     sNu[tid] = nu4;
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -1528,15 +1587,13 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
     const int f = tid / NFP, fn = tid - f * NFP;
     const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
     const bool wall = ((cn.y >> 4) & 15) != 0;
-    R n[3], sMvMI;
-    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + tid) * 4, n, sMvMI);
-    const R w = sMvMI * sNu[vm];
+    const V2 g1 = reinterpret_cast<const V2 *>(A.sgeoP + ((size_t)e * NFN + tid) * 4)[1];
+    const R w = g1.y * sNu[vm];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       // walls: lap+ = lap- (no boundary flux of the Laplacian)
       const R dl = wall ? R(0) : (sLp[s][tid] - sL[s][vm]) * R(0.5);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) sFace[3 * s + d][tid] = w * (n[d] * dl);
+      sLp[s][tid] = w * dl;
     }
   }
   R H[12];
@@ -1559,71 +1616,45 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
       for (int d = 0; d < 3; ++d) H[3 * s + d] = nu4 * ((MI * g[d]) * L1[s] + (MI * g[3 + d]) * L2[s]);
   }
   __syncthreads();
-  R F2[3][5];
-  if (tid < NP) {
-    const int f1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
-    const int f2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
-    if (f1 >= 0) {
+  if (tid >= NP) return;
+  const int fit[2] = {(i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1),
+                      (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1)};
 #pragma unroll
-      for (int c = 0; c < 12; ++c) H[c] += sFace[c][f1];
-    }
-    if (f2 >= 0) {
+  for (int dir = 0; dir < 2; ++dir) {
+    const int it = fit[dir];
+    if (it < 0) continue;
+    R n[3], sMvMI;
+    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
 #pragma unroll
-      for (int c = 0; c < 12; ++c) H[c] += sFace[c][f2];
-    }
-    // viscous part (skipped when the closure is identically zero, as in the GCM drivers'
-    // ConstantKinematicViscosity(0))
-    const bool viscous = P.turbulence == TURB_SMAGORINSKY || P.turb_param != R(0);
-    if (viscous) {
-      R gf[10], gPhi[3] = {0, 0, 0}, Delta = R(0);
-      const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
+    for (int s = 0; s < 4; ++s) {
+      const R w = sLp[s][it];
 #pragma unroll
-      for (int s = 0; s < 10; ++s) gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
-      if (AUX && P.turbulence == TURB_SMAGORINSKY) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
-        Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
-      }
-      flux_second_order<R>(P, q, gf, gPhi, Delta, F2);
-    } else {
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) F2[d][c] = R(0);
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) F2[d][1 + c] += q[0] * H[d + 3 * c];
-      F2[d][4] += (H[d] * q[1] + H[d + 3] * q[2] + H[d + 6] * q[3]) + H[9 + d] * q[0];
+      for (int d = 0; d < 3; ++d) H[3 * s + d] += n[d] * w;
     }
   }
-  __syncthreads();   // face terms consumed: the buffer now stages F2
-  if (tid < NP) {
-    const size_t eoffF = (size_t)e * 12 * NP + tid;
+  // viscous part (skipped when the closure is identically zero, as in the GCM drivers'
+  // ConstantKinematicViscosity(0))
+  R F2[3][5];
+  if (viscous) {
+    flux_second_order<R>(P, q, gf, gPhi, Delta, F2);
+  } else {
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
-      for (int c = 1; c < 5; ++c) {
-        A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
-        sF2[4 * d + c - 1][tid] = F2[d][c];
-      }
+      for (int c = 0; c < 5; ++c) F2[d][c] = R(0);
   }
-  __syncthreads();
-  for (int it = tid; it < NFN; it += BLOCK) {
-    const int f = it / NFP, fn = it - f * NFP;
-    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
-    R n[3], sMvMI;
-    load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
-    typename Vec2<R>::type o0, o1;
-    o0.x = n[0] * sF2[0][vm] + n[1] * sF2[4][vm] + n[2] * sF2[8][vm];
-    o0.y = n[0] * sF2[1][vm] + n[1] * sF2[5][vm] + n[2] * sF2[9][vm];
-    o1.x = n[0] * sF2[2][vm] + n[1] * sF2[6][vm] + n[2] * sF2[10][vm];
-    o1.y = n[0] * sF2[3][vm] + n[1] * sF2[7][vm] + n[2] * sF2[11][vm];
-    typename Vec2<R>::type *po = reinterpret_cast<typename Vec2<R>::type *>(A.Fn + ((size_t)e * NFN + it) * 4);
-    po[0] = o0;
-    po[1] = o1;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) F2[d][1 + c] += q[0] * H[d + 3 * c];
+    F2[d][4] += (H[d] * q[1] + H[d + 3] * q[2] + H[d + 6] * q[3]) + H[9 + d] * q[0];
   }
+  const size_t eoffF = (size_t)e * 12 * NP + tid;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int c = 1; c < 5; ++c) A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
+  write_normal_flux<R, NQ>(A.sgeoP, A.Fn, e, i, j, k, F2);
 }
 
 // ---------------------------------------------------------------------------------------

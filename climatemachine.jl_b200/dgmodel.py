@@ -348,6 +348,15 @@ class DGModel:
         ms = _lib.lib().cmdg_last_kernel_ms(self._h, C.byref(n))
         return float(ms), int(n.value)
 
+    def kernel_class_ms(self):
+        """Device ms and launch count per kernel class of the last fused-stepper call."""
+        out = {}
+        for i, name in enumerate(("tendency", "gradient", "hyper_divergence", "hyper_flux")):
+            n = C.c_int64(0)
+            ms = _lib.lib().cmdg_kernel_class_ms(self._h, i, C.byref(n))
+            out[name] = (float(ms), int(n.value))
+        return out
+
     def sync(self):
         _lib.check(_lib.lib().cmdg_sync(self._h), self._h)
 

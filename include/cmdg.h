@@ -290,6 +290,11 @@ int64_t cmdg_kernel_launches(cmdg_handle h);
  * (CUDA events on the launching stream); returns <0 if timing was not enabled. */
 int cmdg_set_timing(cmdg_handle h, int32_t enable);
 double cmdg_last_kernel_ms(cmdg_handle h, int64_t *nlaunches_out);
+/* The same split by kernel class: tendency (dg_tendency_kernel / hb_tendency_kernel), gradient pass
+ * (dg_gradient_kernel), and the two DryBiharmonic passes. */
+enum { CMDG_KCLASS_TENDENCY = 0, CMDG_KCLASS_GRADIENT = 1, CMDG_KCLASS_HYPER_DIVERGENCE = 2,
+       CMDG_KCLASS_HYPER_FLUX = 3, CMDG_KCLASS_COUNT = 4 };
+double cmdg_kernel_class_ms(cmdg_handle h, int32_t kclass, int64_t *nlaunches_out);
 
 #ifdef __cplusplus
 }
