@@ -115,6 +115,16 @@ def init_state_auxiliary(model, grid, exchange=None):
     if "ref_p" in lay:
         prof = model.ref_state.virtual_temperature_profile
         z = a[:nr, lay["Φ"]] / p.grav
+        if isinstance(prof, bl.DryAdiabaticProfile):
+            Γ = p.grav / p.cp_d
+            Tv = torch.clamp(prof.T_surface - Γ * z, min=prof.T_min_ref)
+            pr = p.MSLP * (Tv / prof.T_surface) ** (p.grav / (p.R_d * Γ))
+            if prof.T_min_ref > 0:
+                z_top = (prof.T_surface - prof.T_min_ref) / Γ
+                H_min = p.R_d * prof.T_min_ref / p.grav
+                pr = torch.where(Tv == prof.T_min_ref, pr * torch.exp(-(z - z_top) / H_min), pr)
+            prof = None
+    if "ref_p" in lay and prof is not None:
         H_sfc = p.R_d * prof.T_virt_surf / p.grav
         zp = z / prof.H_t
         th = torch.tanh(zp)
@@ -124,6 +134,7 @@ def init_state_auxiliary(model, grid, exchange=None):
         pr = -prof.H_t * (zp + dTvp * (torch.log(1 - dTvp * th) - torch.log(1 + th) + zp))
         pr = pr / (H_sfc * (1 - dTvp ** 2))
         pr = p.MSLP * torch.exp(pr)
+    if "ref_p" in lay:
         a[:nr, lay["ref_p"]] = pr
         a[:nr, lay["ref_ρ"]] = pr / (Tv * p.R_d)
         ex(aux)

@@ -81,8 +81,15 @@ class DecayingTemperatureProfile:
 
 
 @dataclass(frozen=True)
+class DryAdiabaticProfile:
+    """``DryAdiabaticProfile{FT}(param_set, T_surface, T_min_ref)`` (TemperatureProfiles.jl:43-98)."""
+    T_surface: float = 290.0
+    T_min_ref: float = 220.0
+
+
+@dataclass(frozen=True)
 class HydrostaticState:
-    virtual_temperature_profile: DecayingTemperatureProfile
+    virtual_temperature_profile: object
     relative_humidity: float = 0.0
     subtract_off: bool = True
 

@@ -401,7 +401,9 @@ __device__ __forceinline__ void extended_sources(const AtmosParams<R> &P, const 
     const R z = Phi / P.grav;
     if (z >= P.sponge_z_sponge) {
       const R r = (z - P.sponge_z_sponge) / (P.sponge_z_max - P.sponge_z_sponge);
-      const R beta = P.sponge_alpha_max * pow_<R>(sinpi_<R>(r / 2), P.sponge_gamma);
+      const R sn = sinpi_<R>(r / 2);
+      // gamma = 2 in every driver of the reference: a product instead of pow (uniform branch)
+      const R beta = P.sponge_alpha_max * (P.sponge_gamma == R(2) ? sn * sn : pow_<R>(sn, P.sponge_gamma));
 #pragma unroll
       for (int d = 0; d < 3; ++d) src[1 + d] += -beta * (q[1 + d] - q[0] * P.sponge_u[d]);
     }

@@ -475,6 +475,43 @@ def decaying_temperature_profile(ps, z, T_virt_surf, T_min_ref, H_t):
     return Tv, p
 
 
+def dry_adiabatic_profile(ps, z, T_surface, T_min_ref):
+    """``DryAdiabaticProfile`` (src/Atmos/TemperatureProfiles/TemperatureProfiles.jl:76-98)."""
+    Γ = ps.grav / ps.cp_d
+    T = np.maximum(T_surface - Γ * z, T_min_ref)
+    p = ps.MSLP * (T / T_surface) ** (ps.grav / (ps.R_d * Γ))
+    z_top = (T_surface - T_min_ref) / Γ
+    H_min = ps.R_d * T_min_ref / ps.grav if T_min_ref != 0 else np.inf
+    with np.errstate(invalid="ignore", divide="ignore"):
+        p = np.where(T == T_min_ref, p * np.exp(-(z - z_top) / H_min), p)
+    return T, p
+
+
+def reference_profile(ps, rs, z, FT):
+    """(T_v, p) of the reference state's temperature profile; ``rs["profile"]`` selects it
+    (default: DecayingTemperatureProfile)."""
+    if rs.get("profile", "decaying") == "dry_adiabatic":
+        return dry_adiabatic_profile(ps, z, FT(rs["T_surf"]), FT(rs["T_min"]))
+    return decaying_temperature_profile(ps, z, FT(rs["T_surf"]), FT(rs["T_min"]), FT(rs["H_t"]))
+
+
+def init_risingbubble(model, aux, xc=5000.0, zc=2000.0, rc=2000.0, θamplitude=2.0):
+    """``init_risingbubble!`` (tutorials/Atmos/risingbubble.jl:106-176) without the tracers."""
+    ps = model.ps
+    FT = aux.dtype.type
+    x, z = aux[0], aux[2]
+    r = np.sqrt((x - FT(xc)) ** 2 + (z - FT(zc)) ** 2)
+    θ_ref = FT(model.ref_state["T_surf"])
+    Δθ = np.where(r <= rc, FT(θamplitude) * (1.0 - r / FT(rc)), FT(0))
+    θ = θ_ref + Δθ
+    π_exner = FT(1) - ps.grav / (ps.cp_d * θ) * z
+    ρ = ps.MSLP / (ps.R_d * θ) * π_exner ** (ps.cv_d / ps.R_d)
+    T = θ * π_exner
+    ρe = ρ * total_energy(ps, FT(0), aux[model.a_Φ], T)
+    zero = np.zeros_like(ρ)
+    return np.stack([ρ, zero, zero, zero, ρe]).astype(FT)
+
+
 def init_baroclinic_wave(model, aux):
     """Dry branch of ``experiments/TestCase/baroclinic_wave.jl:31-163``.
 

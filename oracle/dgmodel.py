@@ -120,8 +120,7 @@ class DGModel:
                 a = _sv(aux.data)
                 nr = g.nreal
                 z = a[bl.a_Φ][:nr] / ps.grav
-                Tv, p = A.decaying_temperature_profile(ps, z, bl.FT(rs["T_surf"]), bl.FT(rs["T_min"]),
-                                                       bl.FT(rs["H_t"]))
+                Tv, p = A.reference_profile(ps, rs, z, bl.FT)
                 a[bl.a_ref["p"]][:nr] = p
                 a[bl.a_ref["ρ"]][:nr] = p / (Tv * ps.R_d)
             ghost_exchange(self.state_auxiliary)

@@ -47,9 +47,11 @@ def device_model(om):
     if om.ref_state is None:
         ref = P.NoReferenceState()
     else:
-        ref = P.HydrostaticState(P.DecayingTemperatureProfile(om.ref_state["T_surf"], om.ref_state["T_min"],
-                                                            om.ref_state["H_t"]),
-                                 subtract_off=om.ref_state.get("subtract_off", True))
+        if om.ref_state.get("profile", "decaying") == "dry_adiabatic":
+            prof = P.DryAdiabaticProfile(om.ref_state["T_surf"], om.ref_state["T_min"])
+        else:
+            prof = P.DecayingTemperatureProfile(om.ref_state["T_surf"], om.ref_state["T_min"], om.ref_state["H_t"])
+        ref = P.HydrostaticState(prof, subtract_off=om.ref_state.get("subtract_off", True))
     k = om.turbulence
     turb = {"constant_dynamic": lambda: P.ConstantDynamicViscosity(float(k[1]), bool(k[2])),
             "constant_kinematic": lambda: P.ConstantKinematicViscosity(float(k[1]), bool(k[2])),
@@ -153,7 +155,7 @@ def vortex_case(nelem=(5, 5, 1), nf="rusanov", nsteps=1, FT=np.float64, skip_zer
     return res
 
 
-def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity):
+def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity, diffusion_direction="every"):
     """Float32 conditioning check: evaluate the oracle in Float64 on the *same Float32 inputs*
     (grid arrays and state upcast) and report the Float32 oracle's and libcmdg's errors
     against that truth.  The isentropic vortex lives on a 0.1 m box, so a Float32 tendency
@@ -168,8 +170,14 @@ def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity):
                                turbulence=model.turbulence, sources=model.sources, bcs=model.bcs)
     out = {}
     tend = {}
+    aux32 = odg.DGModel(model, [g], nf, skip_zero_viscosity=skip_zero_viscosity,
+                        diffusion_direction=diffusion_direction).state_auxiliary[0].data
     for name, gg, mm in (("truth", g64, m64), ("oracle32", g, model)):
-        dgm = odg.DGModel(mm, [gg], nf, skip_zero_viscosity=skip_zero_viscosity)
+        dgm = odg.DGModel(mm, [gg], nf, skip_zero_viscosity=skip_zero_viscosity,
+                          diffusion_direction=diffusion_direction)
+        if name == "truth":
+            # same Float32 auxiliary state, upcast (the reference state is part of the input)
+            dgm.state_auxiliary[0].data[...] = aux32.astype(np.float64)
         q = omsa.MPIStateArray.from_grid(gg, 5)
         np.moveaxis(q.data[:gg.nreal], 1, 0)[...] = Q0
         omsa.ghost_exchange([q])
@@ -177,7 +185,7 @@ def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity):
         dgm([dq], [q], 0.0, 1, 0)
         tend[name] = dq.realdata.astype(np.float64)
         if name == "oracle32":
-            dg, dgrid = make_device_dg(dgm, gg, nf, skip_zero_viscosity=skip_zero_viscosity)
+            dg, dgrid = make_device_dg(dgm, gg, nf, diffusion_direction, skip_zero_viscosity)
             dQ = P.MPIStateArray(dgrid, 5, data=q.data)
             dT = P.MPIStateArray(dgrid, 5)
             dg(dT, dQ, None, 0.0, 1.0, 0.0)
@@ -351,14 +359,61 @@ def bubble_state(model, g, aux):
 
 
 def box_case(nf="rusanov", nsteps=1, dt=0.01, turbulence=("smagorinsky", 0.21),
-             diffusion_direction="every", nelem=(3, 2, 3)):
-    model, gs = box_setup(nelem, turbulence=turbulence)
+             diffusion_direction="every", nelem=(3, 2, 3), FT=np.float64):
+    model, gs = box_setup(nelem, FT=FT, turbulence=turbulence)
     g = gs[0]
     odgm = odg.DGModel(model, [g], nf, diffusion_direction=diffusion_direction)
     aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
     Q0 = bubble_state(model, g, aux)
-    return compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
-                        diffusion_direction=diffusion_direction)
+    res = compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt,
+                       diffusion_direction=diffusion_direction)
+    if FT == np.float32:
+        res.update(float32_truth_errors(model, g, Q0, nf, False, diffusion_direction))
+    return res
+
+
+def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="rusanov"):
+    """BASELINE.json configs[0], tutorials/Atmos/risingbubble.jl as shipped minus the four passive
+    tracers (SURVEY 8.0 note): 10 km x 500 m x 10 km box, periodic x / y, free-slip walls in z, N = 4,
+    SmagorinskyLilly(C_smag = 0.21), HydrostaticState(DryAdiabaticProfile(300 K, 0 K)), Gravity,
+    Rusanov, the tutorial's warm-bubble initial state, LSRK144NiegemannDiehlBusch (the tutorial's
+    mesh is 20 x 1 x 20 elements of 500 m; `nelem` coarsens it for the CPU oracle)."""
+    P = pkg()
+    br = (np.linspace(0, 10000, nelem[0] + 1), np.linspace(0, 500, nelem[1] + 1),
+          np.linspace(0, 10000, nelem[2] + 1))
+    topos = tp.StackedBrickTopology(1, br, periodicity=(True, True, False), boundary=((0, 0), (0, 0), (1, 2)))
+    g = ogrids.Grid(topos[0], 4, FT=FT)
+    model = oatmos.DryAtmosModel(
+        FT, orientation="flat",
+        ref_state=dict(profile="dry_adiabatic", T_surf=300.0, T_min=0.0, H_t=0.0, subtract_off=True),
+        turbulence=("smagorinsky", 0.21), sources=("gravity",), bcs=("freeslip", "freeslip"))
+    odgm = odg.DGModel(model, [g], nf)
+    aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    Q0 = oatmos.init_risingbubble(model, aux)
+    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
+    omsa.ghost_exchange([oQ])
+    dg, dgrid = make_device_dg(odgm, g, nf)
+    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    odQ = oQ.similar()
+    odgm([odQ], [oQ], 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 5)
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    res = {"tendency_rel_l2": rel_l2(dT.realdata.cpu().numpy(), odQ.realdata),
+           "gradflux_rel_l2": rel_l2(dg.state_gradient_flux.realdata.cpu().numpy(),
+                                     odgm.state_gradient_flux[0].realdata)}
+    Q_init = oQ.realdata.copy()
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, [oQ], dt=dt, t0=0.0)
+    oode.solve([oQ], osol, numberofsteps=nsteps)
+    dsol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=dt, t0=0.0)
+    P.solve(dQ, dsol, numberofsteps=nsteps)
+    got = dQ.realdata.cpu().numpy()
+    res["state_rel_l2"] = rel_l2(got, oQ.realdata)
+    # relative to what the steps changed (the state itself is dominated by the hydrostatic background)
+    res["change_rel_l2"] = rel_l2(got - Q_init, oQ.realdata - Q_init)
+    res["launches"] = dg.kernel_launches()
+    dg.close()
+    return res
 
 
 def hyperdiffusion_case(kind="sphere", nsteps=2, turbulence=("constant_kinematic", 0.0, False),

@@ -90,6 +90,16 @@ def test_viscous_box_second_order_path(turbulence, dd):
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+def test_rising_bubble_lsrk144():
+    """BASELINE.json configs[0] (tutorials/Atmos/risingbubble.jl) minus the passive tracers:
+    Smagorinsky LES box, DryAdiabaticProfile reference state, LSRK144."""
+    res = parity.risingbubble_case(nsteps=2)
+    assert res["gradflux_rel_l2"] <= 1e-12, res
+    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
+    assert res["state_rel_l2"] <= 1e-13, res
+    assert res["change_rel_l2"] <= 1e-9, res
+
+
 def test_held_suarez_like_smagorinsky_sphere():
     """Config (4) numerics at test size: Smagorinsky on the cubed sphere, horizontal diffusion
     direction as the GCM experiments set it (parity unpinned in the reference; oracle only)."""

@@ -137,6 +137,38 @@ def test_grid_arrays_cubed_sphere_and_aux(nranks):
         assert np.allclose(Q, np.moveaxis(oQ, 0, 1), rtol=1e-9, atol=1e-9)
 
 
+def test_aux_box_dry_adiabatic_and_hyperdiffusion_lengthscale():
+    """Host-side auxiliary initialisation of the LES box (DryAdiabaticProfile reference state of the
+    rising-bubble tutorial, Smagorinsky Delta) and the DryBiharmonic horizontal length scale against
+    the oracle."""
+    from oracle import atmos as oatmos, dgmodel as odg
+    br = (np.linspace(0, 4000, 4), np.linspace(0, 500, 2), np.linspace(0, 6000, 5))
+    ot = otp.StackedBrickTopology(1, br, periodicity=(True, True, False), boundary=((0, 0), (0, 0), (1, 2)))[0]
+    og = ogrids.Grid(ot, 4)
+    pg = pgrids.build_grid(ptp.stacked_brick_topology(br, (True, True, False), ((0, 0), (0, 0), (1, 2)), 0, 1),
+                           4, device="cpu")
+    for prof, oref, pref in (
+            ("dry_adiabatic", dict(profile="dry_adiabatic", T_surf=300.0, T_min=0.0, H_t=0.0),
+             P.DryAdiabaticProfile(300.0, 0.0)),
+            ("dry_adiabatic_capped", dict(profile="dry_adiabatic", T_surf=300.0, T_min=270.0, H_t=0.0),
+             P.DryAdiabaticProfile(300.0, 270.0)),
+            ("decaying", dict(T_surf=300.0, T_min=220.0, H_t=8e3), P.DecayingTemperatureProfile(300.0, 220.0, 8e3))):
+        om = oatmos.DryAtmosModel(np.float64, orientation="flat", ref_state=dict(oref, subtract_off=True),
+                                  turbulence=("smagorinsky", 0.21), sources=("gravity",),
+                                  bcs=("freeslip", "freeslip"), hyperdiffusion=("dry_biharmonic", 3600.0))
+        odgm = odg.DGModel(om, [og], "rusanov", diffusion_direction="horizontal")
+        pm = P.AtmosModel(orientation=P.FlatOrientation(), ref_state=P.HydrostaticState(pref),
+                          turbulence=P.SmagorinskyLilly(0.21), source=(P.Gravity(),),
+                          boundaryconditions=(P.AtmosBC(), P.AtmosBC()), hyperdiffusion=P.DryBiharmonic(3600.0))
+        assert pm.number_states("Auxiliary") == om.A and pm.number_states("Gradient") == om.G
+        pa = pinit.init_state_auxiliary(pm, pg).data.numpy()
+        oa = odgm.state_auxiliary[0].data
+        scale = np.abs(oa).max(axis=(0, 2), keepdims=True) + 1e-300
+        scale[:, om.a_gradΦ] = np.abs(oa[:, om.a_gradΦ]).max()   # horizontal grad Phi is round-off noise
+        err = np.abs(pa - oa) / scale
+        assert err[:, :-2].max() < 1e-10, (prof, err.max(axis=(0, 2)))
+
+
 def test_vortex_initial_condition():
     from oracle import atmos as oatmos
     br = tuple(np.linspace(-0.05, 0.05, n + 1) for n in (3, 3, 2))
