@@ -465,6 +465,8 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
       if (lo >= 0 && hi > lo)
         prefetch_l2_bulk(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R));
+      // HeldSuarezForcing reads the coordinates (latitude)
+      if (SRCX) prefetch_l2_bulk(auxg + (size_t)en * P.naux * NP, (size_t)3 * NP * sizeof(R));
     }
     if (VISC) {
       prefetch_l2_bulk(A.F2 + (size_t)en * 12 * NP, (size_t)12 * NP * sizeof(R));
@@ -480,10 +482,15 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   R g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   R Phi = 0, pref = 0, rref = 0;
   R gPhi[3] = {0, 0, 0};
+  R xc[3] = {0, 0, 0};
   R f2[12];
   if (tid < NP) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = Qg[eoffQ + (size_t)s * NP + tid];
+    if (AUX && SRCX) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xc[d] = auxg[eoffA + (size_t)d * NP + tid];
+    }
     if (AUX) {
       if (P.a_Phi >= 0) Phi = auxg[eoffA + (size_t)P.a_Phi * NP + tid];
       if (P.a_ref_p >= 0) pref = auxg[eoffA + (size_t)P.a_ref_p * NP + tid];
@@ -587,14 +594,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       src[2] -= P.two_Omega * q[1];
     }
     if (AUX && SRCX) {
-      R x[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) x[d] = auxg[eoffA + (size_t)d * NP + tid];
       if (!(P.sources & SRC_GRAVITY)) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) gPhi[d] = auxg[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
       }
-      extended_sources<R>(P, q, th, Phi, gPhi, x, src);
+      extended_sources<R>(P, q, th, Phi, gPhi, xc, src);
     }
   }
   __syncthreads();

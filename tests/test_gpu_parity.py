@@ -90,6 +90,18 @@ def test_viscous_box_second_order_path(turbulence, dd):
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+def test_viscous_box_float32():
+    """Float32 (the LES drivers' usual precision) on the second-order path: tendency <= 1e-5 against
+    the Float32 oracle, and no further from a Float64 evaluation of the same Float32 inputs than the
+    Float32 oracle itself (x1.25); the gradient-flux array differentiates O(1e5) enthalpies, so its
+    Float32 rounding level is ~1e-4."""
+    res = parity.box_case(nsteps=2, FT=np.float32)
+    assert res["tendency_rel_l2"] <= TOL_TEND_F32, res
+    assert res["state_rel_l2"] <= TOL_TEND_F32, res
+    assert res["gradflux_rel_l2"] <= 5e-4, res
+    assert res["cuda32_vs_truth"] <= 1.25 * res["oracle32_vs_truth"], res
+
+
 def test_rising_bubble_lsrk144():
     """BASELINE.json configs[0] (tutorials/Atmos/risingbubble.jl) minus the passive tracers:
     Smagorinsky LES box, DryAdiabaticProfile reference state, LSRK144."""
