@@ -484,10 +484,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (c10d's "NCCL version ..."
+    # banner on the first communicator) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
