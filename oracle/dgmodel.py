@@ -524,6 +524,7 @@ class DGModel:
         if single:
             tendency, Q = [tendency], [Q]
         bl = self.bl
+        bl.t = t                                # time-dependent sources / boundary states (InitStateBC)
         self.update_auxiliary_state(Q, "real")
         ghost_exchange(Q)                       # begin_ghost_exchange!(Q)
         second = bl.GF > 0 and not self._skip2()

@@ -416,6 +416,46 @@ def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="ru
     return res
 
 
+def balance_case(config="GCM", nf="roe", nsteps=10):
+    """test/Atmos/Model/discrete_hydrostatic_balance.jl on the device: the reference state
+    (subtract_off = false, Gravity) must stay put.  Returns the device's and the oracle's relative
+    drift after `nsteps` LSRK54 steps and their mutual difference."""
+    from tests.test_oracle_balance import _grid, HEIGHT  # noqa: F401
+    P = pkg()
+    ps = oatmos.Params(np.float64)
+    g, orientation = _grid(config)
+    T_surf = float(ps.T_surf_ref)
+    model = oatmos.DryAtmosModel(np.float64, orientation=orientation,
+                                 ref_state=dict(T_surf=T_surf, T_min=float(ps.T_min_ref),
+                                                H_t=float(ps.R_d) * T_surf / float(ps.grav), subtract_off=False),
+                                 turbulence=("constant_dynamic", 0.0, False), sources=("gravity",),
+                                 bcs=("freeslip", "freeslip"))
+    odgm = odg.DGModel(model, [g], nf, skip_zero_viscosity=True)
+    aux = odgm.state_auxiliary[0].data
+    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    oQ.data[:, 0] = aux[:, model.a_ref["ρ"]]
+    oQ.data[:, 4] = aux[:, model.a_ref["ρe"]]
+    Q0 = oQ.data.copy()
+    vg = g.vgeo[:g.nreal]
+    x = np.stack([vg[:, ogrids._x1], vg[:, ogrids._x2], vg[:, ogrids._x3]], axis=-1).reshape(g.nreal, 5, 5, 5, 3)
+    dmin = min(np.linalg.norm(np.diff(x, axis=ax), axis=-1).min() for ax in (1, 2, 3))
+    dt = 0.1 * dmin / float(oatmos.soundspeed_air(ps, np.float64(T_surf)))
+    dg, dgrid = make_device_dg(odgm, g, nf, skip_zero_viscosity=True)
+    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    osol = oode.LSRK54CarpenterKennedy(odgm, [oQ], dt=dt, t0=0.0)
+    oode.solve([oQ], osol, numberofsteps=nsteps)
+    dsol = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt, t0=0.0)
+    P.solve(dQ, dsol, numberofsteps=nsteps)
+    got = dQ.realdata.cpu().numpy()
+    M = vg[:, ogrids._M][:, None, :]
+    nrm = np.sqrt(np.sum(M * Q0[:g.nreal] ** 2))
+    res = {"device_drift": float(np.sqrt(np.sum(M * (got - Q0[:g.nreal]) ** 2)) / nrm),
+           "oracle_drift": float(np.sqrt(np.sum(M * (oQ.realdata - Q0[:g.nreal]) ** 2)) / nrm),
+           "state_rel_l2": rel_l2(got, oQ.realdata)}
+    dg.close()
+    return res
+
+
 def hyperdiffusion_case(kind="sphere", nsteps=2, turbulence=("constant_kinematic", 0.0, False),
                         tau=None, nf="rusanov"):
     """DryBiharmonic(tau) with diffusion_direction = HorizontalDirection(), as the GCM

@@ -90,6 +90,18 @@ def test_viscous_box_second_order_path(turbulence, dd):
     assert res["state_rel_l2"] <= 1e-12, res
 
 
+@pytest.mark.parametrize("config,nf", [("GCM", "roe"), ("LES", "central")])
+def test_discrete_hydrostatic_balance_on_device(config, nf):
+    """The reference's property test test/Atmos/Model/discrete_hydrostatic_balance.jl through libcmdg:
+    initialised to the discretely balanced reference state (subtract_off = false, Gravity) the state
+    does not drift (the reference's bar is 100 eps; the device folds the mass matrix into its packed
+    metric terms, so its rounding pattern differs: bar 1e-12) and equals the oracle's to 1e-13."""
+    res = parity.balance_case(config, nf)
+    assert res["oracle_drift"] <= 100 * np.finfo(np.float64).eps, res
+    assert res["state_rel_l2"] <= 1e-13, res
+    assert res["device_drift"] <= 1e-12, res
+
+
 def test_viscous_box_float32():
     """Float32 (the LES drivers' usual precision) on the second-order path: tendency <= 1e-5 against
     the Float32 oracle, and no further from a Float64 evaluation of the same Float32 inputs than the
