@@ -427,7 +427,7 @@ def cpu_baseline(workload, budget_s=15.0, ne=None, nvert=10):
     t0 = time.perf_counter()
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 1)
     one = time.perf_counter() - t0
-    n = max(1, min(200, int(budget_s / max(one, 1e-6))))
+    n = max(1, min(2000, int(budget_s / max(one, 1e-6))))
     t0 = time.perf_counter()
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, n)
     el = time.perf_counter() - t0

@@ -74,7 +74,8 @@ class MPIStateArray:
         if data is None:
             self.data = torch.zeros((grid.nelem, nstate, grid.Np), dtype=grid.FT, device=grid.device)
         else:
-            self.data = torch.as_tensor(np.ascontiguousarray(data)).to(grid.device).to(grid.FT)
+            # own copy (on a CPU device torch would otherwise alias the caller's NumPy buffer)
+            self.data = torch.as_tensor(np.array(data, order="C", copy=True)).to(grid.device).to(grid.FT)
             assert self.data.shape == (grid.nelem, nstate, grid.Np)
 
     @property
