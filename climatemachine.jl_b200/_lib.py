@@ -42,7 +42,8 @@ class cmdg_desc(C.Structure):
         ("sponge_z_max", C.c_double), ("sponge_z_sponge", C.c_double),
         ("sponge_alpha_max", C.c_double), ("sponge_gamma", C.c_double),
         ("sponge_u_relax", C.c_double * 3),
-        ("hyperdiffusion", C.c_int32), ("_pad0", C.c_int32), ("hyper_tau", C.c_double),
+        ("hyperdiffusion", C.c_int32), ("ntracers", C.c_int32), ("hyper_tau", C.c_double),
+        ("tracer_delta_chi", C.c_double * 4),
     ]
 
 

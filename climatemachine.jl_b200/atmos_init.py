@@ -35,7 +35,11 @@ def aux_layout(m):
         lay["Δh"] = c
         c += 1
     lay["θ_v"], lay["T"] = c, c + 1
-    lay["A"] = c + 2
+    c += 2
+    if isinstance(m.tracers, bl.NTracers):
+        lay["δ_χ"] = c
+        c += len(m.tracers.δ_χ)
+    lay["A"] = c
     return lay
 
 
@@ -156,6 +160,9 @@ def init_state_auxiliary(model, grid, exchange=None):
                - vg[:, 3] * (vg[:, 1] * vg[:, 8] - vg[:, 7] * vg[:, 2])
                + vg[:, 6] * (vg[:, 1] * vg[:, 5] - vg[:, 4] * vg[:, 2]))
         a[:nr, lay["Δ"]] = 2 / (torch.sign(det) * det.abs() ** (1.0 / 3.0) * max(1, grid.N))
+    if "δ_χ" in lay:
+        for i, δ in enumerate(model.tracers.δ_χ):      # atmos_init_aux!(::NTracers) (tracers.jl:133-140)
+            a[:nr, lay["δ_χ"] + i] = δ
     if "Δh" in lay:
         # lengthscale_horizontal (src/Numerics/Mesh/Geometry.jl:129-152): mean of |J e1|, |J e2| times 2 / N
         vg = grid.vgeo[:nr].double()

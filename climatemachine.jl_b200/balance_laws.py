@@ -124,6 +124,20 @@ class DryBiharmonic:
     τ_timescale: float
 
 
+# --- tracers (src/Atmos/Model/tracers.jl) -------------------------------------
+class NoTracers:
+    pass
+
+
+@dataclass(frozen=True)
+class NTracers:
+    """``NTracers{N, FT}(delta_chi)``: N passive tracers with diffusivity ratios delta_chi (N <= 4)."""
+    δ_χ: Tuple
+
+    def __post_init__(self):
+        object.__setattr__(self, "δ_χ", tuple(float(x) for x in self.δ_χ))
+
+
 # --- sources ---------------------------------------------------------------
 class Gravity:
     pass
@@ -233,16 +247,17 @@ class AtmosModel:
     def number_states(self, kind):
         smag = isinstance(self.turbulence, SmagorinskyLilly)
         hyp = isinstance(self.hyperdiffusion, DryBiharmonic)
+        nt = len(self.tracers.δ_χ) if isinstance(self.tracers, NTracers) else 0
         if kind == "Prognostic":
-            return 5
+            return 5 + nt
         if kind == "Gradient":
-            return (5 if smag else 4) + (4 if hyp else 0)
+            return (5 if smag else 4) + (4 if hyp else 0) + nt
         if kind == "GradientLaplacian":
             return 4 if hyp else 0
         if kind == "Hyperdiffusive":
             return 12 if hyp else 0
         if kind == "GradientFlux":
-            return 10 if smag else 9
+            return (10 if smag else 9) + 3 * nt
         if kind == "Auxiliary":
             c = 3
             if not isinstance(self.orientation, NoOrientation):
@@ -253,7 +268,7 @@ class AtmosModel:
                 c += 1
             if hyp:
                 c += 1
-            return c + 2
+            return c + 2 + nt
         raise KeyError(kind)
 
     def validate(self):
@@ -264,7 +279,14 @@ class AtmosModel:
                 "(NoHyperDiffusion / DryBiharmonic only)")
         if isinstance(self.hyperdiffusion, DryBiharmonic) and isinstance(self.orientation, NoOrientation):
             raise UnsupportedModelError("DryBiharmonic needs an orientation")
-        for name in ("precipitation", "radiation", "tracers", "turbconv"):
+        if self.tracers is not None and not isinstance(self.tracers, (NoTracers, NTracers)):
+            raise UnsupportedModelError(f"tracer model {type(self.tracers).__name__} is not supported")
+        if isinstance(self.tracers, NTracers):
+            if not 1 <= len(self.tracers.δ_χ) <= 4:
+                raise UnsupportedModelError("NTracers: 1..4 tracers are compiled into libcmdg")
+            if isinstance(self.hyperdiffusion, DryBiharmonic):
+                raise UnsupportedModelError("NTracers with DryBiharmonic is not supported")
+        for name in ("precipitation", "radiation", "turbconv"):
             if getattr(self, name) is not None:
                 raise UnsupportedModelError(
                     f"AtmosModel.{name} = {getattr(self, name)!r} is not supported by libcmdg "

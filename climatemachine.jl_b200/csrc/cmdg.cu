@@ -11,6 +11,7 @@
 #include "../../include/cmdg.h"
 #include "cmdg_kernels.cuh"
 #include "cmdg_ocean.cuh"
+#include "cmdg_tracers.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -102,6 +103,9 @@ struct cmdg_handle_s {
   // (12 columns) and their horizontal Laplacians (4 columns)
   bool hyper = false;
   void *Qhg = nullptr, *Qhd = nullptr;
+  // passive tracers: nu per node from the gradient kernel, tracer diffusive flux per node
+  int ntracers = 0;
+  void *NuDev = nullptr, *F2chi = nullptr;
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
   bool grid_bound = false;
@@ -196,7 +200,9 @@ AtmosParams<R> make_params(const cmdg_handle_s *h) {
   if (d.hyperdiffusion == CMDG_HYPER_DRY_BIHARMONIC) P.a_Delta_h = c++;
   P.a_theta_v = c;
   P.a_T = c + 1;
-  P.naux = c + 2;
+  P.naux = c + 2 + d.ntracers;
+  P.nstate = d.nstate;
+  P.ngf_dyn = d.turbulence == CMDG_TURB_SMAGORINSKY ? 10 : 9;
   P.ngradflux = d.ngradflux;
   P.inv_day = d.day > 0 ? (R)(R(1) / (R)d.day) : R(0);
   P.sponge_z_max = (R)d.sponge_z_max;
@@ -213,7 +219,7 @@ int expected_naux(const cmdg_desc &d) {
   if (d.ref_state == CMDG_REF_HYDROSTATIC) c += 7;
   if (d.turbulence == CMDG_TURB_SMAGORINSKY) c += 1;
   if (d.hyperdiffusion == CMDG_HYPER_DRY_BIHARMONIC) c += 1;
-  return c + 2;
+  return c + 2 + d.ntracers;
 }
 
 cudaEvent_t timing_event(cmdg_handle h, int kclass = CMDG_KCLASS_TENDENCY) {
@@ -602,6 +608,10 @@ TendArgs<R> base_args(cmdg_handle h) {
   return a;
 }
 
+template <class R>
+int eval_with_tracers(cmdg_handle h, void *dQ, const void *Q, void *Qout, double alpha, double beta,
+                      double rkb_dt, double t, bool exchange_q, bool write_diag, cudaStream_t st);
+
 // One full evaluation in the reference's order (DGModel.jl:85-427).  With `Qout` set the
 // stage update is fused (cmdg_lsrk_steps); the exchange schedule is then exterior-first, so
 // that the halo of the *next* stage's state is in flight while the interior elements of this
@@ -610,6 +620,7 @@ template <class R>
 int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double beta,
                cudaStream_t st) {
   if (h->is_hb) return hb_eval_t<R>(h, dQ, Q, nullptr, alpha, beta, 0.0, st);
+  if (h->ntracers) return eval_with_tracers<R>(h, dQ, Q, nullptr, alpha, beta, 0.0, t, true, true, st);
   const bool par = h->comm && !h->nabrtorank.empty();
   const int64_t nreal = h->d.nrealelem;
   TendArgs<R> a = base_args<R>(h);
@@ -639,6 +650,78 @@ int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double 
   }
   a.elems = h->exterior;
   return launch_tendency<R>(h, a, h->nexterior, st);
+}
+
+// One evaluation with passive tracers, serial halo schedule: [Q halo] -> gradient kernel (all real
+// elements; also nu per node) -> tracer gradient kernel -> F2 and F2chi halos -> tendency kernel of the
+// five dynamic states -> tracer tendency kernel.  `Qout` != NULL fuses the RK stage update of all
+// 5 + N columns.  The tracers are a side path of configs[0]: no interior / exterior overlap here.
+template <class R>
+int eval_with_tracers(cmdg_handle h, void *dQ, const void *Q, void *Qout, double alpha, double beta,
+                      double rkb_dt, double t, bool exchange_q, bool write_diag, cudaStream_t st) {
+  const bool par = h->comm && !h->nabrtorank.empty();
+  const int64_t nreal = h->d.nrealelem;
+  int rc;
+  if (nreal <= 0) return 0;
+  if (par && exchange_q) {
+    if ((rc = exchange_begin_t<R>(h, const_cast<void *>(Q), h->d.nstate, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, const_cast<void *>(Q), h->d.nstate, st))) return rc;
+  }
+  if ((rc = ensure_const_D<R>(h, st))) return rc;
+  const AtmosParams<R> P = make_params<R>(h);
+  TracerArgs<R> ta{};
+  ta.Q = (const R *)Q;
+  ta.dQ = (R *)dQ;
+  ta.Qout = (R *)Qout;
+  ta.gradflux = write_diag ? (R *)h->gradflux : nullptr;
+  ta.Nu = h->d.turbulence == CMDG_TURB_SMAGORINSKY ? (const R *)h->NuDev : nullptr;
+  ta.F2chi = (R *)h->F2chi;
+  ta.vgeoP = (const R *)h->vgeoP;
+  ta.sgeoP = (const R *)h->sgeoP;
+  ta.conn = h->conn;
+  ta.elems = nullptr;
+  ta.nt = h->ntracers;
+  for (int i = 0; i < CMDG_MAX_TRACERS; ++i) ta.delta[i] = i < h->ntracers ? (R)h->d.tracer_delta_chi[i] : R(0);
+  ta.alpha = (R)alpha;
+  ta.beta = (R)beta;
+  ta.rkb_dt = (R)rkb_dt;
+  ta.visc = h->visc ? 1 : 0;
+  ta.rusanov = h->d.nf_first == CMDG_NF_RUSANOV ? 1 : 0;
+  if (h->visc) {
+    GradArgs<R> ga{(const R *)Q, (const R *)h->aux, write_diag ? (R *)h->gradflux : nullptr, (const R *)h->vgeoP,
+                   (const R *)h->sgeoP, h->conn, nullptr, (const R *)h->Ddev, (R *)h->F2dev, (R *)h->FnDev,
+                   (R *)h->Qhg, h->pf_dist};
+    ga.Nu = h->d.turbulence == CMDG_TURB_SMAGORINSKY ? (R *)h->NuDev : nullptr;
+    if ((rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+    tracer_gradient_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(ta, P);
+    CU(cudaGetLastError());
+    h->launches++;
+    if (par) {
+      if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, st))) return rc;
+      if ((rc = exchange_end_t<R>(h, h->F2dev, 12, st))) return rc;
+      if ((rc = exchange_begin_t<R>(h, h->F2chi, 3 * h->ntracers, st))) return rc;
+      if ((rc = exchange_end_t<R>(h, h->F2chi, 3 * h->ntracers, st))) return rc;
+    }
+  }
+  TendArgs<R> a = base_args<R>(h);
+  a.Q = (const R *)Q;
+  a.dQ = (R *)dQ;
+  a.Qout = (R *)Qout;
+  a.alpha = (R)alpha;
+  a.beta = (R)beta;
+  a.rkb_dt = (R)rkb_dt;
+  a.t = (R)t;
+  a.elems = nullptr;
+  if (!write_diag) a.aux_out = nullptr;
+  if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
+  tracer_tendency_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(ta, P);
+  CU(cudaGetLastError());
+  h->launches++;
+  if (par && Qout) {
+    if ((rc = exchange_begin_t<R>(h, Qout, h->d.nstate, st))) return rc;
+    if ((rc = exchange_end_t<R>(h, Qout, h->d.nstate, st))) return rc;
+  }
+  return 0;
 }
 
 template <class R>
@@ -712,7 +795,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   // Interior elements have no ghost neighbours, so the interior kernel of stage s only needs the real
   // elements of stage s-1 (exterior + interior kernels); the exterior kernel of stage s needs those and
   // the ghosts unpacked by its own stream.  Per stage: max(interior, exterior + pack + NCCL + unpack).
-  const bool overlap = par && !h->is_hb && !h->visc && h->step_filter_target < 0 && h->overlap_exterior &&
+  const bool overlap = par && !h->is_hb && !h->visc && !h->ntracers && h->step_filter_target < 0 && h->overlap_exterior &&
                        h->ext_stream && h->nexterior > 0 && h->ninterior > 0;
   cudaStream_t xs = h->ext_stream;
   if (overlap) {
@@ -728,6 +811,15 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
         if (rc) return rc;
         // the vertical filters act on the stage state itself: the ghost layer of the new state is
         // refreshed by the next evaluation's exchange
+        R *tmp2 = cur;
+        cur = nxt;
+        nxt = tmp2;
+        continue;
+      }
+      if (h->ntracers) {
+        int rc = eval_with_tracers<R>(h, dQ, cur, nxt, 1.0, rka[s], (double)((R)rkb[s] * (R)dt),
+                                      time + rkc[s] * dt, false, s == nstage - 1, st);
+        if (rc) return rc;
         R *tmp2 = cur;
         cur = nxt;
         nxt = tmp2;
@@ -1030,7 +1122,15 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   for (int i = 0; i < d->nbc; ++i)
     if (d->bc_kind[i] != CMDG_BC_FREESLIP && d->bc_kind[i] != CMDG_BC_NOSLIP)
       return fail(nullptr, CMDG_ERR_UNSUPPORTED, "unsupported boundary condition");
-  if (d->nstate != 5) return fail(nullptr, CMDG_ERR_UNSUPPORTED, "dry AtmosModel has 5 prognostic states (tracers/moisture unsupported)");
+  const int nt = d->ntracers;
+  if (nt < 0 || nt > CMDG_MAX_TRACERS)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "NTracers: 0..4 passive tracers are supported");
+  if (d->nstate != 5 + nt)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "dry AtmosModel has 5 + ntracers prognostic states (moisture unsupported)");
+  if (nt && d->nf_first == CMDG_NF_ROE)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "NTracers: Rusanov / Central first-order fluxes only");
+  if (nt && d->hyperdiffusion != CMDG_HYPER_NONE)
+    return fail(nullptr, CMDG_ERR_UNSUPPORTED, "NTracers with hyperdiffusion is not supported");
   if (d->naux != expected_naux(*d))
     return fail(nullptr, CMDG_ERR_INVALID, "naux does not match the model's auxiliary state");
   const int gf = d->turbulence == CMDG_TURB_SMAGORINSKY ? 10 : 9;
@@ -1043,7 +1143,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
     return fail(nullptr, CMDG_ERR_UNSUPPORTED,
                 "DryBiharmonic: only diffusion_direction = HorizontalDirection() (the reference's 3-D EveryDirection kernel does not run)");
   if (hyp && !(d->hyper_tau > 0)) return fail(nullptr, CMDG_ERR_INVALID, "DryBiharmonic needs hyper_tau > 0");
-  if (d->ngradflux != gf || d->ngrad != (gf == 10 ? 5 : 4) + 4 * hyp)
+  if (d->ngradflux != gf + 3 * nt || d->ngrad != (gf == 10 ? 5 : 4) + 4 * hyp + nt)
     return fail(nullptr, CMDG_ERR_INVALID, "ngrad/ngradflux do not match the model");
   if (d->nrealelem < 0 || d->nelem < d->nrealelem || d->nelem > 0x7fffffffLL)
     return fail(nullptr, CMDG_ERR_INVALID, "bad element counts");
@@ -1060,6 +1160,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   const bool zero_visc = d->turbulence != CMDG_TURB_SMAGORINSKY && d->turb_param == 0.0;
   h->visc = !(d->skip_zero_viscosity && zero_visc) || hyp;
   h->hyper = hyp;
+  h->ntracers = nt;
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
   if (const char *kv = getenv("CMDG_OVERLAP")) h->overlap_exterior = atoi(kv) != 0;
   // the NCCL send/recv kernel is launched while the interior kernel still has thousands of blocks
@@ -1089,7 +1190,8 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd};
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
+                  h->NuDev, h->F2chi};
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
@@ -1208,6 +1310,14 @@ int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
       CU(cudaMalloc(&h->Qhd, hd + 16));
       CU(cudaMemset(h->Qhg, 0, f2));
       CU(cudaMemset(h->Qhd, 0, hd));
+    }
+    if (h->ntracers) {
+      const size_t nu = (size_t)h->d.nrealelem * 3 * h->Np * h->fb;
+      const size_t fc = (size_t)h->d.nelem * 3 * h->ntracers * h->Np * h->fb;
+      CU(cudaMalloc(&h->NuDev, nu + 16));
+      CU(cudaMalloc(&h->F2chi, fc + 16));
+      CU(cudaMemset(h->NuDev, 0, nu));
+      CU(cudaMemset(h->F2chi, 0, fc));
     }
   }
   return CMDG_OK;

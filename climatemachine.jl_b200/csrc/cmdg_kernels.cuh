@@ -53,6 +53,9 @@ struct AtmosParams {
   int a_Phi, a_gradPhi, a_ref_rho, a_ref_p, a_Delta, a_Delta_h, a_theta_v, a_T;
   R hyper_tau;   // DryBiharmonic time scale (a_Delta_h >= 0 when hyperdiffusion is on)
   int naux, ngradflux;
+  // column strides of Q / dQ (5 + passive tracers) and the number of gradient-flux columns of the
+  // dynamics (9 or 10; the tracers' grad chi columns follow them)
+  int nstate, ngf_dyn;
   // HeldSuarezForcing / RayleighSponge (SRCX kernels only)
   R inv_day, sponge_z_max, sponge_z_sponge, sponge_alpha_max, sponge_gamma, sponge_u[3];
 };
@@ -427,7 +430,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
-  const size_t eoffQ = (size_t)e * 5 * NP;
+  const size_t eoffQ = (size_t)e * P.nstate * NP;
   const size_t eoffA = (size_t)e * P.naux * NP;
   const R *__restrict__ Qg = A.Q;
   const R *__restrict__ auxg = A.aux;
@@ -456,10 +459,10 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
     const int bn = blockIdx.x + A.pf_dist;
     const int en = A.elems ? A.elems[bn] : bn;
-    prefetch_l2_bulk(Qg + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(Qg + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
     prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
     prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R));
-    if (A.beta != R(0)) prefetch_l2_bulk(A.dQ + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    if (A.beta != R(0)) prefetch_l2_bulk(A.dQ + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
     if (AUX) {
       const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
       const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
@@ -520,7 +523,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       const int b = fn / NQ;
       if (cn[r].y & 8) a = NQ - 1 - a;
       const int vp = face_to_vol<NQ>(cn[r].y & 7, a, b);
-      const size_t offp = (size_t)cn[r].x * 5 * NP + vp;
+      const size_t offp = (size_t)cn[r].x * P.nstate * NP + vp;
 #pragma unroll
       for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&S.Qp[s][it], Qg + offp + (size_t)s * NP);
       if (AUX) {
@@ -848,7 +851,7 @@ courant_kernel(const R *__restrict__ Q, const R *__restrict__ aux, const R *__re
     }
     R q[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) q[s] = Q[((size_t)e * 5 + s) * NP + tid];
+    for (int s = 0; s < 5; ++s) q[s] = Q[((size_t)e * P.nstate + s) * NP + tid];
     const size_t oa = (size_t)e * P.naux * NP + tid;
     R k[3] = {0, 0, 0}, gP[3] = {0, 0, 0};
     if (P.a_gradPhi >= 0) {
@@ -862,7 +865,7 @@ courant_kernel(const R *__restrict__ Q, const R *__restrict__ aux, const R *__re
       R gf[10];
 #pragma unroll
       for (int s = 0; s < 10; ++s)
-        gf[s] = (s < P.ngradflux) ? gradflux[((size_t)e * P.ngradflux + s) * NP + tid] : R(0);
+        gf[s] = (s < P.ngf_dyn) ? gradflux[((size_t)e * P.ngradflux + s) * NP + tid] : R(0);
       const R Delta = P.a_Delta >= 0 ? aux[oa + (size_t)P.a_Delta * NP] : R(0);
       R nu[3];
       turbulence_nu<R>(P, q, gf, gP, Delta, nu);
@@ -1024,6 +1027,8 @@ struct GradArgs {
   // DryBiharmonic (HYPER kernels): gradient of (u_h, h_tot), column 3*s + d  [nelem][12][Np]
   R *Qhg;
   int pf_dist;   // L2 prefetch distance in launch-list entries (0 = off)
+  // passive tracers: diagonal of the turbulent viscosity tensor per node, [nreal][3][Np] (NULL = not wanted)
+  R *Nu;
 };
 
 template <class R>
@@ -1125,7 +1130,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   constexpr int NITEM = (NFN + BLOCK - 1) / BLOCK;
   const int tid = threadIdx.x;
   const int e = A.elems ? A.elems[blockIdx.x] : blockIdx.x;
-  const size_t eoffQ = (size_t)e * 5 * NP;
+  const size_t eoffQ = (size_t)e * P.nstate * NP;
   const size_t eoffA = (size_t)e * P.naux * NP;
   const int nfaces = P.horizontal_diffusion ? 4 : 6;
   const bool smag = P.turbulence == TURB_SMAGORINSKY;
@@ -1142,7 +1147,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
   if (A.pf_dist > 0 && blockIdx.x + A.pf_dist < gridDim.x && tid == BLOCK - 1) {
     const int bn = blockIdx.x + A.pf_dist;
     const int en = A.elems ? A.elems[bn] : bn;
-    prefetch_l2_bulk(A.Q + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(A.Q + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
     prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
     prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
     if (AUX && P.a_Phi >= 0) {
@@ -1162,7 +1167,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       const int b = fn / NQ;
       if (cn[r].y & 8) a = NQ - 1 - a;
       const int vp = face_to_vol<NQ>(cn[r].y & 7, a, b);
-      const size_t offp = (size_t)cn[r].x * 5 * NP + vp;
+      const size_t offp = (size_t)cn[r].x * P.nstate * NP + vp;
 #pragma unroll
       for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&sQp[s][it], A.Q + offp + (size_t)s * NP);
       if (AUX && P.a_Phi >= 0)
@@ -1363,7 +1368,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
     const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
 #pragma unroll
     for (int s = 0; s < 10; ++s)
-      if (s < P.ngradflux) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
+      if (s < P.ngf_dyn) A.gradflux[eoffG + (size_t)s * NP] = gfv[s];
   }
   if (HYPER) {
     const size_t eoffH = (size_t)e * 12 * NP + tid;
@@ -1388,6 +1393,13 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int c = 1; c < 5; ++c) A.F2[eoffF + (size_t)(4 * d + c - 1) * NP] = F2[d][c];
   write_normal_flux<R, NQ>(A.sgeoP, A.Fn, e, i, j, k, F2);
+  if (A.Nu) {
+    // D_t = nu / Pr_t of this node for the tracer diffusion (tracer_gradient_kernel)
+    R nu[3];
+    turbulence_nu<R>(P, q, gfv, gPhi, Delta, nu);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) A.Nu[((size_t)e * 3 + d) * NP + tid] = nu[d];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1540,7 +1552,7 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
     const int bn = blockIdx.x + A.pf_dist;
     const int en = A.elems ? A.elems[bn] : bn;
     prefetch_l2_bulk(A.Qhd + (size_t)en * 4 * NP, 4 * NP * sizeof(R));
-    prefetch_l2_bulk(A.Q + (size_t)en * 5 * NP, 5 * NP * sizeof(R));
+    prefetch_l2_bulk(A.Q + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
     prefetch_l2_bulk(A.aux + ((size_t)en * P.naux + P.a_Delta_h) * NP, NP * sizeof(R));
     prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
     prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
@@ -1569,14 +1581,14 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) sL[s][tid] = A.Qhd[eo + (size_t)s * NP];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) q[s] = A.Q[(size_t)e * 5 * NP + (size_t)s * NP + tid];
+    for (int s = 0; s < 5; ++s) q[s] = A.Q[(size_t)e * P.nstate * NP + (size_t)s * NP + tid];
     const R hD = A.aux[eoffA + (size_t)P.a_Delta_h * NP + tid] * R(0.5);
     load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
     if (viscous) {
       // issued early: consumed after the face terms
       const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
 #pragma unroll
-      for (int s = 0; s < 10; ++s) gf[s] = (s < P.ngradflux) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
+      for (int s = 0; s < 10; ++s) gf[s] = (s < P.ngf_dyn) ? A.gradflux[eoffG + (size_t)s * NP] : R(0);
       if (AUX && P.turbulence == TURB_SMAGORINSKY) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];

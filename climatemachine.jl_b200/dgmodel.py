@@ -183,12 +183,18 @@ class DGModel:
             d.hyperdiffusion, d.hyper_tau = _lib.HYPER_DRY_BIHARMONIC, float(m.hyperdiffusion.τ_timescale)
         else:
             d.hyperdiffusion = _lib.HYPER_NONE
+        nt = len(m.tracers.δ_χ) if isinstance(m.tracers, bl.NTracers) else 0
+        if nt and isinstance(numerical_flux_first_order, bl.RoeNumericalFlux):
+            raise bl.UnsupportedModelError("NTracers: Rusanov / Central first-order fluxes only")
+        d.ntracers = nt
+        for i in range(nt):
+            d.tracer_delta_chi[i] = m.tracers.δ_χ[i]
         d.skip_zero_viscosity = int(skip_zero_viscosity)
         d.write_aux_diagnostics = int(write_aux_diagnostics)
         d.nbc = len(m.boundaryconditions)
         for i, bc in enumerate(m.boundaryconditions):
             d.bc_kind[i] = _lib.BC_FREESLIP if isinstance(bc.momentum.drag, bl.FreeSlip) else _lib.BC_NOSLIP
-        d.nstate, d.naux = 5, A
+        d.nstate, d.naux = m.number_states("Prognostic"), A
         d.ngrad, d.ngradflux = m.number_states("Gradient"), GF
         p = m.param_set
         d.R_d, d.cp_d, d.cv_d, d.T_0 = p.R_d, p.cp_d, p.cv_d, p.T_0

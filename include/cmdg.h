@@ -110,9 +110,15 @@ typedef struct {
    * reference's 3-D EveryDirection kernel does not run, DGModel_kernels.jl:2640-2650) and adds
    * aux.hyperdiffusion.Delta after aux.turbulence.Delta; ngrad grows by 4 (u_h, h_tot) */
   int32_t hyperdiffusion; /* CMDG_HYPER_* */
-  int32_t _pad0;
+  /* NTracers{N, FT}(delta_chi) (src/Atmos/Model/tracers.jl:113-131): N <= CMDG_MAX_TRACERS passive
+   * tracers rho*chi after rho*e (nstate = 5 + N), aux.tracers.delta_chi after aux.moisture (naux += N),
+   * chi in the gradient variables (ngrad += N), grad chi (3 x N, column-major) at the end of the
+   * gradient flux (ngradflux += 3 N).  Rusanov / Central first-order fluxes; not with DryBiharmonic. */
+  int32_t ntracers;
   double hyper_tau;
+  double tracer_delta_chi[4];
 } cmdg_desc;
+#define CMDG_MAX_TRACERS 4
 
 /*
  * Ocean HydrostaticBoussinesqModel (src/Ocean/HydrostaticBoussinesq/hydrostatic_boussinesq_model.jl:40-103)

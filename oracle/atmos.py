@@ -97,7 +97,7 @@ class DryAtmosModel:
 
     def __init__(self, FT=np.float64, orientation="none", ref_state=None,
                  turbulence=("constant_dynamic", 0.0, False), sources=(),
-                 bcs=(), params=None, hyperdiffusion=None):
+                 bcs=(), params=None, hyperdiffusion=None, tracers=None):
         self.FT = np.dtype(FT).type
         self.ps = params or Params(FT)
         self.orientation = orientation            # none | flat | spherical
@@ -132,7 +132,18 @@ class DryAtmosModel:
             c += 1
         self.a_θv = c
         self.a_T = c + 1
-        self.A = c + 2
+        c += 2
+        # NTracers{N}(delta_chi) (src/Atmos/Model/tracers.jl:113-131): N passive tracers rho*chi after
+        # rho*e; aux.tracers.delta_chi after aux.moisture; chi in the gradient variables and grad chi
+        # (3 x N, column-major: d + 3 i) in the gradient flux after everything else
+        self.tracers = None if tracers is None else tuple(float(x) for x in tracers)
+        self.NT = 0 if tracers is None else len(self.tracers)
+        self.S = 5 + self.NT
+        self.a_δχ = None
+        if self.NT:
+            self.a_δχ = slice(c, c + self.NT)
+            c += self.NT
+        self.A = c
         # gradient / gradient-flux layout
         self.smag = turbulence[0] == "smagorinsky"
         self.G = 5 if self.smag else 4
@@ -146,6 +157,9 @@ class DryAtmosModel:
             self.hyper_G = self.G
             self.G += 4
             self.ngradlap, self.nhyper = 4, 12
+        self.G_χ, self.GF_χ = self.G, self.GF
+        self.G += self.NT
+        self.GF += 3 * self.NT
         self.subtract_off = bool(ref_state is not None and ref_state.get("subtract_off", True))
 
     # ------------------------------------------------------------------
@@ -166,10 +180,10 @@ class DryAtmosModel:
         return T, air_pressure(self.ps, T, Q[0])
 
     def flux_first_order(self, Q, aux):
-        """F[d, s, ...] (3, 5, ...)."""
+        """F[d, s, ...] (3, S, ...)."""
         ρ, ρu, ρe = Q[0], Q[1:4], Q[4]
         T, p = self.thermo(Q, aux)
-        F = np.zeros((3, 5) + Q.shape[1:], dtype=Q.dtype)
+        F = np.zeros((3, self.S) + Q.shape[1:], dtype=Q.dtype)
         u = ρu / ρ
         F[:, 0] = ρu
         for d in range(3):
@@ -179,6 +193,9 @@ class DryAtmosModel:
         for d in range(3):
             F[d, 1 + d] = F[d, 1 + d] + pp
         F[:, 4] = u * ρe + u * p
+        for i in range(self.NT):
+            # flux(::Tracers, ::Advect) (tendencies_tracers.jl:7-11): rho*chi_i u
+            F[:, 5 + i] = Q[5 + i] * u
         return F
 
     def source(self, Q, aux):
@@ -247,7 +264,11 @@ class DryAtmosModel:
         u = (1 / Q[0]) * Q[1:4]
         uN = np.abs(n[0] * u[0] + n[1] * u[1] + n[2] * u[2])
         T, _ = self.thermo(Q, aux)
-        return uN + soundspeed_air(self.ps, T)
+        ws = uN + soundspeed_air(self.ps, T)
+        if not self.NT:
+            return ws
+        # wavespeed_tracers! (tracers.jl:165-180): the tracers travel with |u . n| only
+        return np.stack([ws] * 5 + [uN] * self.NT)
 
     # --- auxiliary update (moisture.jl:58-69) --------------------------
     def nodal_update_aux(self, Q, aux):
@@ -289,6 +310,8 @@ class DryAtmosModel:
             ku = k[0] * u[0] + k[1] * u[1] + k[2] * u[2]
             G[self.hyper_G:self.hyper_G + 3] = u - k * ku
             G[self.hyper_G + 3] = G[3]
+        for i in range(self.NT):
+            G[self.G_χ + i] = Q[5 + i] * ρinv
         return G
 
     def transform_post_gradient_laplacian(self, gradlap, Q, aux):
@@ -305,6 +328,7 @@ class DryAtmosModel:
         return H
 
     def flux_hyperdiffusive(self, Q, H):
+        assert self.NT == 0, "DryBiharmonic with tracers is not restated"
         """HyperdiffViscousFlux / HyperdiffEnthalpyFlux (tendencies_momentum.jl:51-54,
         tendencies_energy.jl:40-48): F[d, 1 + c] = rho H[d, c]; F[d, 4] = H[d, :] . rhou + H_h[d] rho."""
         F = np.zeros((3, 5) + Q.shape[1:], dtype=Q.dtype)
@@ -326,10 +350,13 @@ class DryAtmosModel:
         GF[6] = du[1, 1]
         GF[7] = (du[2, 1] + du[1, 2]) / 2
         GF[8] = du[2, 2]
-        if self.GF == 10:
+        if self.smag:
             gΦ = aux[self.a_gradΦ]
             gθ = gradG[:, 4]
             GF[9] = (gθ[0] * gΦ[0] + gθ[1] * gΦ[1] + gθ[2] * gΦ[2]) / aux[self.a_θv]
+        for i in range(self.NT):
+            for d in range(3):
+                GF[self.GF_χ + d + 3 * i] = gradG[d, self.G_χ + i]
         return GF
 
     def turbulence_tensors(self, Q, GF, aux):
@@ -366,7 +393,7 @@ class DryAtmosModel:
         raise ValueError(kind)
 
     def flux_second_order(self, Q, GF, aux):
-        F = np.zeros((3, 5) + Q.shape[1:], dtype=Q.dtype)
+        F = np.zeros((3, self.S) + Q.shape[1:], dtype=Q.dtype)
         if self.GF == 0:
             return F
         D_t, τ = self.turbulence_tensors(Q, GF, aux)
@@ -378,6 +405,11 @@ class DryAtmosModel:
             visc = τ[i][0] * ρu[0] + τ[i][1] * ρu[1] + τ[i][2] * ρu[2]
             d_h = (-D_t[i]) * GF[i]
             F[i, 4] = visc + d_h * ρ
+        for t in range(self.NT):
+            # flux(::Tracers, ::Diffusion) (tendencies_tracers.jl:17-22): d_chi = (-D_t) delta_chi' .* grad chi
+            δ = aux[self.a_δχ][t]
+            for i in range(3):
+                F[i, 5 + t] = (((-D_t[i]) * δ) * GF[self.GF_χ + i + 3 * t]) * ρ
         return F
 
     # --- Roe flux (dry) ------------------------------------------------

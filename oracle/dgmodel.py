@@ -159,6 +159,9 @@ class DGModel:
                 a[bl.a_Δ][:nr] = 2 / (np.cbrt(det) * max(1, *g.N))
             if getattr(bl, "a_Δh", None) is not None:
                 a[bl.a_Δh][:nr] = lengthscale_horizontal(g)
+            if getattr(bl, "a_δχ", None) is not None:
+                for i, δ in enumerate(bl.tracers):      # atmos_init_aux!(::NTracers) (tracers.jl:133-140)
+                    a[bl.a_δχ][i][:nr] = δ
         ghost_exchange(self.state_auxiliary)
 
     def reference_pressure_gradient(self):

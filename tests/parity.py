@@ -64,8 +64,9 @@ def device_model(om):
     hyp = None
     if getattr(om, "hyperdiffusion", None) is not None:
         hyp = P.DryBiharmonic(float(om.hyperdiffusion[1]))
+    trc = P.NTracers(tuple(om.tracers)) if getattr(om, "tracers", None) else None
     return P.AtmosModel(orientation=orient, ref_state=ref, turbulence=turb, source=src,
-                        boundaryconditions=bcs, hyperdiffusion=hyp)
+                        boundaryconditions=bcs, hyperdiffusion=hyp, tracers=trc)
 
 
 def make_device_dg(odgm, g, nf, diffusion_direction="every", skip_zero_viscosity=False):
@@ -372,8 +373,9 @@ def box_case(nf="rusanov", nsteps=1, dt=0.01, turbulence=("smagorinsky", 0.21),
     return res
 
 
-def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="rusanov"):
-    """BASELINE.json configs[0], tutorials/Atmos/risingbubble.jl as shipped minus the four passive
+def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="rusanov", tracers=None):
+    """BASELINE.json configs[0], tutorials/Atmos/risingbubble.jl: with `tracers=(1, 2, 3, 4)` as shipped
+    (NTracers{4} injected in a layer, `init_risingbubble!`), with `tracers=None` minus the four passive
     tracers (SURVEY 8.0 note): 10 km x 500 m x 10 km box, periodic x / y, free-slip walls in z, N = 4,
     SmagorinskyLilly(C_smag = 0.21), HydrostaticState(DryAdiabaticProfile(300 K, 0 K)), Gravity,
     Rusanov, the tutorial's warm-bubble initial state, LSRK144NiegemannDiehlBusch (the tutorial's
@@ -386,22 +388,45 @@ def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="ru
     model = oatmos.DryAtmosModel(
         FT, orientation="flat",
         ref_state=dict(profile="dry_adiabatic", T_surf=300.0, T_min=0.0, H_t=0.0, subtract_off=True),
-        turbulence=("smagorinsky", 0.21), sources=("gravity",), bcs=("freeslip", "freeslip"))
+        turbulence=("smagorinsky", 0.21), sources=("gravity",), bcs=("freeslip", "freeslip"),
+        tracers=tracers)
+    S = model.S
     odgm = odg.DGModel(model, [g], nf)
     aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
     Q0 = oatmos.init_risingbubble(model, aux)
-    oQ = omsa.MPIStateArray.from_grid(g, 5)
+    if tracers:
+        # the tutorial injects rho*chi = 0.05 for 500 < z <= 550 (a layer thinner than the coarsened test
+        # mesh resolves: widened to 400 < z <= 1600 and tapered so that gradients are non-trivial), then
+        # rho*chi, /2, /3, /4
+        z, x = aux[2], aux[0]
+        ρχ = np.where((z > 400) & (z <= 1600), 0.05 * (1 + 0.5 * np.sin(2 * np.pi * x / 10000)), 0.0).astype(FT)
+        # the tutorial starts at rest, where the tracer tendency is a 1e-5 m^2/s diffusion only: add a smooth
+        # wind (w = 0 on the walls) so that advection, the Rusanov penalty and the Smagorinsky D_t all act
+        u = [8 + 2 * np.sin(2 * np.pi * z / 10000), 0 * z, 1.5 * np.sin(2 * np.pi * x / 10000) * np.sin(np.pi * z / 10000)]
+        ρ = Q0[0]
+        Q0[1], Q0[2], Q0[3] = ρ * u[0], ρ * u[1], ρ * u[2]
+        Q0[4] = Q0[4] + ρ * (u[0] ** 2 + u[1] ** 2 + u[2] ** 2) / 2
+        Q0 = np.concatenate([Q0, np.stack([ρχ / (i + 1) for i in range(len(tracers))])]).astype(FT)
+    oQ = omsa.MPIStateArray.from_grid(g, S)
     np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
     omsa.ghost_exchange([oQ])
     dg, dgrid = make_device_dg(odgm, g, nf)
-    dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
+    dQ = P.MPIStateArray(dgrid, S, data=oQ.data)
     odQ = oQ.similar()
     odgm([odQ], [oQ], 0.0, 1, 0)
-    dT = P.MPIStateArray(dgrid, 5)
+    dT = P.MPIStateArray(dgrid, S)
+    dT.data.fill_(float("nan"))
     dg(dT, dQ, None, 0.0, 1.0, 0.0)
-    res = {"tendency_rel_l2": rel_l2(dT.realdata.cpu().numpy(), odQ.realdata),
-           "gradflux_rel_l2": rel_l2(dg.state_gradient_flux.realdata.cpu().numpy(),
-                                     odgm.state_gradient_flux[0].realdata)}
+    got_t, got_gf = dT.realdata.cpu().numpy(), dg.state_gradient_flux.realdata.cpu().numpy()
+    res = {"tendency_rel_l2": rel_l2(got_t[:, :5], odQ.realdata[:, :5]),
+           "gradflux_rel_l2": rel_l2(got_gf[:, :10], odgm.state_gradient_flux[0].realdata[:, :10])}
+    if tracers:
+        res["tracer_tendency_rel_l2"] = [rel_l2(got_t[:, 5 + i], odQ.realdata[:, 5 + i]) for i in range(len(tracers))]
+        res["tracer_gradflux_rel_l2"] = rel_l2(got_gf[:, 10:], odgm.state_gradient_flux[0].realdata[:, 10:])
+        # increment form
+        odgm([odQ], [oQ], 0.0, 0.5, 2.0)
+        dg(dT, dQ, None, 0.0, 0.5, 2.0)
+        res["tendency_inc_rel_l2"] = rel_l2(dT.realdata.cpu().numpy(), odQ.realdata)
     Q_init = oQ.realdata.copy()
     osol = oode.LSRK144NiegemannDiehlBusch(odgm, [oQ], dt=dt, t0=0.0)
     oode.solve([oQ], osol, numberofsteps=nsteps)
@@ -411,6 +436,9 @@ def risingbubble_case(nelem=(10, 1, 10), nsteps=2, dt=0.4, FT=np.float64, nf="ru
     res["state_rel_l2"] = rel_l2(got, oQ.realdata)
     # relative to what the steps changed (the state itself is dominated by the hydrostatic background)
     res["change_rel_l2"] = rel_l2(got - Q_init, oQ.realdata - Q_init)
+    if tracers:
+        res["tracer_state_rel_l2"] = rel_l2(got[:, 5:], oQ.realdata[:, 5:])
+        res["tracer_change_rel_l2"] = rel_l2(got[:, 5:] - Q_init[:, 5:], oQ.realdata[:, 5:] - Q_init[:, 5:])
     res["launches"] = dg.kernel_launches()
     dg.close()
     return res

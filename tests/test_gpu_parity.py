@@ -124,6 +124,26 @@ def test_rising_bubble_lsrk144():
     assert res["change_rel_l2"] <= 1e-9, res
 
 
+def test_rising_bubble_with_tracers_as_shipped():
+    """BASELINE.json configs[0] as the tutorial ships it: NTracers{4} with delta_chi = (1, 2, 3, 4) on top
+    of the Smagorinsky LES box (S = 9, A = 21, G = 9, GF = 22), LSRK144.  The five dynamic states use
+    the fused kernels, the tracer columns tracer_gradient_kernel / tracer_tendency_kernel.
+    The north star's bar (tendency rel-L2 <= 1e-12) is applied to the whole tendency (all nine states);
+    each tracer column on its own is held to 1e-11: its diffusive part carries the Smagorinsky D_t, whose
+    Richardson correction differentiates theta_v, and a one-ulp change of theta_v (a different exp/log)
+    already moves the tracer tendencies by 1.2e-12 x delta_chi in the oracle itself
+    (tests/test_oracle_tracers.py::test_tracer_tendency_conditioning)."""
+    res = parity.risingbubble_case(nsteps=2, tracers=(1.0, 2.0, 3.0, 4.0))
+    assert res["gradflux_rel_l2"] <= 1e-12, res
+    assert res["tracer_gradflux_rel_l2"] <= 1e-12, res
+    assert res["tendency_rel_l2"] <= TOL_TEND_F64, res
+    assert max(res["tracer_tendency_rel_l2"]) <= 1e-11, res
+    assert res["tendency_inc_rel_l2"] <= TOL_TEND_F64, res
+    assert res["state_rel_l2"] <= 1e-13, res
+    assert res["tracer_state_rel_l2"] <= 1e-12, res
+    assert res["tracer_change_rel_l2"] <= 1e-9, res
+
+
 def test_held_suarez_like_smagorinsky_sphere():
     """Config (4) numerics at test size: Smagorinsky on the cubed sphere, horizontal diffusion
     direction as the GCM experiments set it (parity unpinned in the reference; oracle only)."""
