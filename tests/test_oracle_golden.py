@@ -102,3 +102,34 @@ def test_lsrk54_order_of_accuracy():
         errs.append(abs(q[0].data[0, 0, 0] - np.exp(a)))
     rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert np.all(np.abs(rates - 4) < 0.3)
+
+
+@pytest.mark.parametrize("method", ["LSRK54CarpenterKennedy", "LSRK144NiegemannDiehlBusch"])
+def test_lsrk_convergence_reference_problem(method):
+    """ode_tests_convergence.jl:15-45 as written there: dq/dt = q cos(t) (time-dependent, so the RKC
+    abscissae matter), exact q0 exp(sin t), final time 20, dt = 2^-6, 2^-7; the observed rate must be
+    within 0.17 of the expected order 4 (`explicit_methods`, ode_tests_common.jl:4-5)."""
+    class S:
+        def __init__(self, v=1.0):
+            self.data = np.full((1, 1, 1), v)
+            self.nreal = 1
+
+        @property
+        def realdata(self):
+            return self.data
+
+        def similar(self):
+            return S(0.0)
+
+    def rhs(dQ, Q, t, increment=False):
+        for dq, q in zip(dQ, Q):
+            dq.data[...] = q.data * np.cos(t) + (dq.data if increment else 0)
+
+    errs = []
+    for k in (6, 7):
+        q = [S()]
+        sol = getattr(odesolvers, method)(rhs, q, dt=2.0 ** -k, t0=0.0)
+        odesolvers.solve(q, sol, timeend=20.0)
+        errs.append(abs(q[0].data[0, 0, 0] - np.exp(np.sin(20.0))))
+    rate = np.log2(errs[0] / errs[1])
+    assert abs(rate - 4) <= 0.17, (errs, rate)
