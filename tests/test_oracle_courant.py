@@ -44,3 +44,43 @@ def test_courant_numbers_uniform_flow():
     assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "nondiffusive"), dt * (50.0 + c) / dx, rtol=1e-12)
     assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "advective"), dt * 50.0 / dx, rtol=1e-12)
     assert courant.courant(model, g, Q, aux, GF, dt, "diffusive") == 0.0
+
+
+def test_atmos_courant_reference_known_answers():
+    """test/Numerics/DGMethods/courant.jl (3-D, Float64): AtmosModel (LES config: FlatOrientation),
+    NoReferenceState, ConstantDynamicViscosity(2, WithDivergence()), Gravity; u = (150 x1, 150 x1, 0),
+    T = 300 K, p = 1e5 Pa on the 10 x 10 x 4 stacked brick [0,1]^2 x [1,2], dt = 1/200.  Expected:
+    nondiffusive horizontal = dt (|(150,150,0)| + c_s) / dx_h and vertical = dt c_s / dx_v (rtol 1e-4),
+    diffusive horizontal / vertical = dt (mu / rho) / dx^2 (`isapprox`)."""
+    from oracle import atmos, dgmodel as odg
+    Neh, Nev = 10, 4
+    br = (np.linspace(0, 1, Neh + 1), np.linspace(0, 1, Neh + 1), np.linspace(1, 2, Nev + 1))
+    topo = tp.StackedBrickTopology(1, br, periodicity=(False, False, False), connectivity="full")[0]
+    g = grids.Grid(topo, 4)
+    μ = 2.0
+    model = atmos.DryAtmosModel(np.float64, orientation="flat", ref_state=None,
+                                turbulence=("constant_dynamic", μ, True), sources=("gravity",),
+                                bcs=("freeslip",))
+    ps = model.ps
+    dgm = odg.DGModel(model, [g], "rusanov")
+    aux = dgm.state_auxiliary[0].data
+    T, p = 300.0, 1e5
+    ρ = float(atmos.air_density(ps, np.float64(T), np.float64(p)))
+    x1 = g.vgeo[:, grids._x1]
+    Q = np.zeros((g.nelem, 5, g.Np))
+    u = 150.0 * x1
+    Q[:, 0], Q[:, 1], Q[:, 2] = ρ, ρ * u, ρ * u
+    Q[:, 4] = ρ * atmos.total_energy(ps, (u * u + u * u) / 2, np.float64(0), np.float64(T))
+    GF = dgm.state_gradient_flux[0].data            # the diffusive number of a constant closure ignores it
+    dt = 1 / 200
+    dx_h = courant.min_node_distance(g, "horizontal")
+    dx_v = courant.min_node_distance(g, "vertical")
+    c_s = float(atmos.soundspeed_air(ps, np.float64(T)))
+    c_h = dt * (np.linalg.norm([150.0, 150.0, 0.0]) + c_s) / dx_h
+    c_v = dt * c_s / dx_v
+    d_h = dt * (μ / ρ) / dx_h ** 2
+    d_v = dt * (μ / ρ) / dx_v ** 2
+    assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "nondiffusive", "horizontal"), c_h, rtol=1e-4)
+    assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "nondiffusive", "vertical"), c_v, rtol=1e-4)
+    assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "diffusive", "horizontal"), d_h, rtol=1.5e-8)
+    assert np.isclose(courant.courant(model, g, Q, aux, GF, dt, "diffusive", "vertical"), d_v, rtol=1.5e-8)
