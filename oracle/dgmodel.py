@@ -256,7 +256,7 @@ class DGModel:
             nr = g.nreal
             qs, a = _sv(q.data[:nr]), _sv(aux.data[:nr])
             F = bl.flux_first_order(qs, a)
-            if bl.GF > 0 and not self._skip2():
+            if self._second():
                 F = F + bl.flux_second_order(qs, _sv(gf.data[:nr]), a)
                 if self.nhyper:
                     hg = self.Qhypervisc_grad[self.grids.index(g)]
@@ -273,6 +273,11 @@ class DGModel:
 
     def _skip2(self):
         return self.skip_zero_viscosity and not self.bl.viscous()
+
+    def _second(self):
+        """The gradient / second-order machinery runs when the law has gradient-flux or hyperdiffusive
+        variables (DGModel.jl:118-123: ``num_state_gradient_flux > 0 || nhyperviscstate > 0``)."""
+        return (self.bl.GF > 0 or self.nhyper > 0) and not self._skip2()
 
     # ------------------------------------------------------------------
     # numerical fluxes
@@ -315,7 +320,7 @@ class DGModel:
             elems = (g.interiorelems if which == "interior" else g.exteriorelems) - 1
             if len(elems) == 0:
                 continue
-            second = bl.GF > 0 and not self._skip2()
+            second = self._second()
             for f in range(6):
                 em, vm, ep, vp, bnd = self._face_data(g, elems, f, q.data)
                 n = np.stack([g.sgeo[elems, f, :, c] for c in range(3)])
@@ -530,7 +535,7 @@ class DGModel:
         bl.t = t                                # time-dependent sources / boundary states (InitStateBC)
         self.update_auxiliary_state(Q, "real")
         ghost_exchange(Q)                       # begin_ghost_exchange!(Q)
-        second = bl.GF > 0 and not self._skip2()
+        second = self._second()
         if second:
             self.volume_gradients(Q, t)
             self.interface_gradients(Q, t, "interior")
