@@ -60,6 +60,9 @@ def _desc(P, **kw):
     (dict(sources=16), -2, b"source"),
     (dict(naux=16), -1, b"naux"),
     (dict(float_bytes=2), -2, b"Float64 or Float32"),
+    (dict(ntracers=5, nstate=10), -2, b"NTracers"),
+    (dict(ntracers=2, nstate=7, naux=7, ngrad=6, ngradflux=15, nf_first=2), -2, b"Rusanov / Central"),
+    (dict(ntracers=2, nstate=7, naux=7, ngrad=6, ngradflux=14), -1, b"ngrad/ngradflux"),
 ])
 def test_unsupported_models_raise_not_fallback(P, kw, code, msg):
     h = C.c_void_p()
@@ -76,12 +79,21 @@ def test_no_device_is_an_error_not_a_fallback(P):
     h = C.c_void_p()
     rc = P._lib.lib().cmdg_create(C.byref(_desc(P)), C.byref(h))
     assert rc == -5 and b"no CPU fallback" in P._lib.lib().cmdg_last_error(None)
+    # a valid NTracers{2} descriptor passes validation and stops at the same place
+    rc = P._lib.lib().cmdg_create(C.byref(_desc(P, ntracers=2, nstate=7, naux=7, ngrad=6, ngradflux=15)), C.byref(h))
+    assert rc == -5
 
 
 def test_host_mirror_rejects_unsupported_models(P):
     m = P.AtmosModel(tracers=object())
     with pytest.raises(P.UnsupportedModelError):
         m.validate()
+    with pytest.raises(P.UnsupportedModelError):
+        P.AtmosModel(tracers=P.NTracers((1, 2, 3, 4, 5))).validate()
+    m = P.AtmosModel(orientation=P.FlatOrientation(), ref_state=P.HydrostaticState(P.DryAdiabaticProfile()),
+                     turbulence=P.SmagorinskyLilly(), tracers=P.NTracers((1, 2, 3, 4)))
+    m.validate()   # risingbubble.jl: S, A, G, GF = 9, 21, 9, 22
+    assert [m.number_states(k) for k in ("Prognostic", "Auxiliary", "Gradient", "GradientFlux")] == [9, 21, 9, 22]
     with pytest.raises(P.UnsupportedModelError):
         P.AtmosModel(source=(object(),)).validate()
     assert P.AtmosModel().number_states("Auxiliary") == 5
