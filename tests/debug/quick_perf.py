@@ -2,7 +2,7 @@
 uses the oracle only to build inputs)."""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tests import parity
 from oracle import grids as ogrids, dgmodel as odg
