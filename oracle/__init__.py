@@ -17,14 +17,33 @@ the oracle is pinned against the reference's *own* golden numbers instead:
   (mesh + metrics + DGModel + Rusanov/Central/Roe + LSRK54 + thermodynamic
   constants, end to end), reproduced to ``rtol = sqrt(eps)`` as the test itself
   demands (``tests/test_oracle_golden.py``);
+* ``test/Numerics/DGMethods/compressible_Navier_Stokes/mms_bc_atmos.jl`` -- the second-order
+  (Navier-Stokes) path: 3-D level-1 golden error to 1e-7 (``tests/test_oracle_mms.py``);
+* ``test/Numerics/DGMethods/advection_diffusion/periodic_3D_hyperdiffusion.jl`` -- the
+  hyperdiffusion kernels: 3-D HorizontalDirection level-1 golden error to 1e-7
+  (``tests/test_oracle_hyperdiffusion_golden.py``);
+* ``test/Numerics/DGMethods/grad_test_sphere.jl``, ``grad_test.jl`` -- cubed-sphere metric terms and the
+  element-local gradient (``tests/test_oracle_grad.py``);
+* ``test/Atmos/Model/discrete_hydrostatic_balance.jl`` -- Gravity + HydrostaticState stay balanced to
+  100 eps on the LES box and the GCM shell (``tests/test_oracle_balance.py``);
+* ``test/Numerics/DGMethods/courant.jl``, ``test/Numerics/Mesh/min_node_distance.jl`` -- Courant numbers
+  and node distances (``tests/test_oracle_courant.py``);
+* ``test/Numerics/Mesh/filter.jl`` -- golden filter matrices and the analytic application test
+  (``tests/test_oracle_filters.py``, fixtures in ``tests/golden``);
+* ``test/Ocean/refvals/test_ocean_gyre_refvals.jl`` (short) -- HBModel regression values
+  (``tests/test_oracle_ocean.py``);
+* ``test/Numerics/ODESolvers/ode_tests_convergence.jl`` -- LSRK54 / LSRK144 order 4 on the reference's
+  time-dependent problem;
 * ``test/Numerics/Mesh/mpi_connect*.jl`` -- connectivity / ghost lists on 3-5 ranks
   (bit exact);
 * ``test/Arrays/mpi_comm.jl`` -- halo pack/unpack known answers;
 * ``test/Numerics/Mesh/{Elements,Grids,Metrics}.jl`` -- quadrature / metric identities.
 
-Parts for which the reference holds no tight golden value (Coriolis/gravity on
-the cubed sphere, Smagorinsky on the sphere) are marked "parity unpinned" in
-the module that restates them and in DESIGN.md.
+Parts for which the reference holds no tight golden value are "parity unpinned" (restatement plus
+analytic / property checks only), here and in DESIGN.md section 3: Coriolis, the Smagorinsky-Lilly
+closure itself (its plumbing is pinned by the MMS run), HeldSuarezForcing and RayleighSponge, the
+AtmosModel hooks of DryBiharmonic (its kernels are pinned), NTracers, the rising-bubble configuration
+with DryAdiabaticProfile, the AtmosFilterPerturbations target.
 
 Array convention: every array is stored with the *bytes* Julia would have
 (column-major ``A[i, j, k]`` == C-order ``a[k, j, i]``), so a NumPy array of
