@@ -21,7 +21,8 @@ GOLDEN_F64_3D = {
     ("roe", 1): 4.0766143963611068e+00, ("roe", 2): 4.3942394181655547e-01,
 }
 # expected_error[Float32, 3, flux, 1]  (isentropicvortex.jl:150-238)
-GOLDEN_F32_3D = {("rusanov", 1): 3.7918186187744141e+00}
+GOLDEN_F32_3D = {("rusanov", 1): 3.7918186187744141e+00, ("central", 1): 6.5903329849243164e+00,
+                 ("roe", 1): 4.0765657424926758e+00}
 
 
 def vortex_error(level, nf, FT=np.float64, csize=1):
@@ -133,3 +134,11 @@ def test_lsrk_convergence_reference_problem(method):
         errs.append(abs(q[0].data[0, 0, 0] - np.exp(np.sin(20.0))))
     rate = np.log2(errs[0] / errs[1])
     assert abs(rate - 4) <= 0.17, (errs, rate)
+
+
+@pytest.mark.parametrize("nf", ["rusanov", "central", "roe"])
+def test_isentropic_vortex_float32_level1_golden(nf):
+    """The Float32 rows of the same table (isentropicvortex.jl:195-206): the oracle run entirely in
+    Float32 lands within the test's own gate, rtol = sqrt(eps(Float32)) = 3.5e-4."""
+    err = float(vortex_error(1, nf, FT=np.float32))
+    assert err == pytest.approx(GOLDEN_F32_3D[(nf, 1)], rel=float(np.sqrt(np.finfo(np.float32).eps)))
