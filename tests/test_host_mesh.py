@@ -192,3 +192,15 @@ def test_imat_and_filters_match_oracle():
     assert np.allclose(P.CutoffFilter(pg, 3).filter_matrix, oocean.cutoff_filter_matrix(r, 3), atol=1e-14)
     assert np.allclose(P.ExponentialFilter(pg, 1, 8).filter_matrix,
                        oocean.exponential_filter_matrix(r, 1, 8), atol=1e-14)
+
+
+def test_host_lsrk_tableaus_match_the_pinned_oracle():
+    """The host mirror's LSRK54 / LSRK144 coefficients (what cmdg_lsrk_steps receives) are the oracle's,
+    which the reference's convergence problem pins (tests/test_oracle_golden.py)."""
+    from oracle import odesolvers as oode
+    from climatemachine_jl_b200 import dgmodel as pdg
+    for host, names in ((pdg._LSRK54, ("LSRK54_RKA", "LSRK54_RKB", "LSRK54_RKC")),
+                        (pdg._LSRK144, ("LSRK144_RKA", "LSRK144_RKB", "LSRK144_RKC"))):
+        for h, name in zip(host, names):
+            ref = [float(x) for x in oode._conv(np.float64, getattr(oode, name))]
+            assert [float(x) for x in h] == ref, name
