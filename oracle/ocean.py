@@ -245,18 +245,8 @@ class HBModel:
             Nqh = Nq[0] * Nq[1]
             a[:, self.a_w, :] = -gd[:, 0, :]
             nh = ne // nv
-            Imat = g.Imat[2]
-            JcV = g.vgeo[sl, G._JcV, :].reshape(nh, nv, Nq[2], Nqh)
             kern = np.stack([a[:, self.a_w, :], -self.alphaT * qd[:, 3, :]])
-            kern = kern.reshape(2, nh, nv, Nq[2], Nqh) * JcV[None]
-            out = np.zeros_like(kern)
-            carry = np.zeros((2, nh, Nqh))
-            for ev in range(nv):
-                li = np.repeat(carry[:, :, None, :], Nq[2], axis=2)
-                for n in range(Nq[2]):
-                    li = li + Imat[:, n][None, None, :, None] * kern[:, :, ev, n:n + 1, :]
-                out[:, :, ev] = li
-                carry = li[:, :, Nq[2] - 1, :]
+            out = indefinite_stack_integral(g, kern, sl)
             w = out[0].reshape(ne, g.Np)
             pk = out[1]
             top = pk[:, nv - 1, Nq[2] - 1, :]
@@ -267,6 +257,31 @@ class HBModel:
                 wtop = out[0][:, nv - 1, Nq[2] - 1, :]
                 wz0 = np.broadcast_to(wtop[:, None, None, :], (nh, nv, Nq[2], Nqh))
                 a[:, self.a_wz0, :] = wz0.reshape(ne, g.Np)
+
+
+def indefinite_stack_integral(g, kern, sl=None):
+    """``kernel_indefinite_stack_integral!`` (DGModel_kernels.jl:1903-1990): upward integral of ``kern``
+    (nfields, nelem_in_sl, Np) along every vertical stack, element by element with ``Imat`` (the
+    indefinite-integral interpolation matrix of the vertical LGL points) times ``JcV``, carrying the value
+    at the top node of an element into the next.  Returns (nfields, nstacks, nvertelem, Nq3, Nq1*Nq2)."""
+    sl = slice(0, g.nreal) if sl is None else sl
+    nv = g.topology.stacksize
+    Nq = g.Nq
+    Nqh = Nq[0] * Nq[1]
+    nf, ne = kern.shape[0], kern.shape[1]
+    nh = ne // nv
+    Imat = g.Imat[2]
+    JcV = g.vgeo[sl, G._JcV, :].reshape(nh, nv, Nq[2], Nqh)
+    kern = kern.reshape(nf, nh, nv, Nq[2], Nqh) * JcV[None]
+    out = np.zeros_like(kern)
+    carry = np.zeros((nf, nh, Nqh), dtype=kern.dtype)
+    for ev in range(nv):
+        li = np.repeat(carry[:, :, None, :], Nq[2], axis=2)
+        for n in range(Nq[2]):
+            li = li + Imat[:, n][None, None, :, None] * kern[:, :, ev, n:n + 1, :]
+        out[:, :, ev] = li
+        carry = li[:, :, Nq[2] - 1, :]
+    return out
 
 
 def statecheck(arr, ivar):
