@@ -30,8 +30,10 @@ the oracle is pinned against the reference's *own* golden numbers instead:
   and node distances (``tests/test_oracle_courant.py``);
 * ``test/Numerics/Mesh/filter.jl`` -- golden filter matrices and the analytic application test
   (``tests/test_oracle_filters.py``, fixtures in ``tests/golden``);
-* ``test/Ocean/refvals/test_ocean_gyre_refvals.jl`` (short) -- HBModel regression values
-  (``tests/test_oracle_ocean.py``);
+* ``test/Ocean/refvals/test_ocean_gyre_refvals.jl`` (short) and ``test_windstress_refvals.jl``
+  (explicit_cpu) -- HBModel regression values (``tests/test_oracle_ocean.py``,
+  ``tests/test_oracle_ocean_windstress.py``); ``test/Numerics/DGMethods/integral_test.jl`` -- the stack
+  integral (``tests/test_oracle_integral.py``);
 * ``test/Numerics/ODESolvers/ode_tests_convergence.jl`` -- LSRK54 / LSRK144 order 4 on the reference's
   time-dependent problem;
 * ``test/Numerics/Mesh/mpi_connect*.jl`` -- connectivity / ghost lists on 3-5 ranks
