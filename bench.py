@@ -423,6 +423,7 @@ def cpu_baseline(workload, budget_s=15.0, ne=None, nvert=10):
     sample of the same workload: a coarser horizontal mesh with the same vertical stack."""
     ne = ne or (8 if workload == "baroclinic_wave" else 12)
     c, Q, dQ, aux, dt, rka, rkb, nreal, cref = cpu_case(workload, ne, nvert)
+    cref.use_all_cores()
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 1)       # warm up
     t0 = time.perf_counter()
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 1)
@@ -447,6 +448,7 @@ def run_reference(args):
     import numpy as np
     ne = args.ne or (8 if args.workload == "baroclinic_wave" else 12)
     c, Q, dQ, aux, dt, rka, rkb, nreal, cref = cpu_case(args.workload, ne, args.nvert)
+    cref.use_all_cores()     # torchrun exports OMP_NUM_THREADS=1
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, max(args.warmup, 1))
     t0 = time.perf_counter()
     c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, args.steps)

@@ -78,6 +78,16 @@ int ref_num_threads(void) {
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1; the CPU arm of bench.py asks for every core it
+ * may run on instead. */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void ref_update_aux(const ref_params *P, const double *Q, double *aux, int64_t e0, int64_t e1) {
 #pragma omp parallel for schedule(static)
   for (int64_t e = e0; e < e1; ++e)

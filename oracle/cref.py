@@ -25,7 +25,18 @@ def lib():
             raise RuntimeError(f"{_SO} missing: run `make -C oracle/c` (done by __graft_entry__.build())")
         _lib = C.CDLL(_SO)
         _lib.ref_num_threads.restype = C.c_int
+        _lib.ref_set_num_threads.argtypes = [C.c_int]
     return _lib
+
+
+def use_all_cores():
+    """All host cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().ref_set_num_threads(n)
+    return n
 
 
 def params_from_model(model, nf="rusanov"):
