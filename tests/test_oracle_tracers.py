@@ -106,3 +106,37 @@ def test_tracer_tendency_conditioning():
     trc = [parity.rel_l2(dq2.realdata[:, 5 + i], dq.realdata[:, 5 + i]) for i in range(4)]
     assert dyn < 1e-13
     assert 1e-14 < max(trc) < 1e-10, trc
+
+
+def test_emulated_ranks_agree_with_tracers():
+    """3 emulated ranks (Hilbert partition, ghost exchange of the 9-column state and of the 22-column
+    gradient flux) reproduce the single-rank tendency, tracers included."""
+    def run(csize):
+        br = (np.linspace(0, 1500, 4), np.linspace(0, 1000, 4), np.linspace(0, 1500, 4))
+        topos = tp.StackedBrickTopology(csize, br, periodicity=(True, True, False),
+                                        boundary=((0, 0), (0, 0), (1, 2)))
+        gs = [ogrids.Grid(t, 4) for t in topos]
+        m = oatmos.DryAtmosModel(np.float64, orientation="flat",
+                                 ref_state=dict(T_surf=300.0, T_min=220.0, H_t=8e3, subtract_off=True),
+                                 turbulence=("smagorinsky", 0.21), sources=("gravity",),
+                                 bcs=("freeslip", "noslip"), tracers=(1.0, 2.0, 3.0, 4.0))
+        dgm = odg.DGModel(m, gs, "rusanov")
+        Q = []
+        for g, aux in zip(gs, dgm.state_auxiliary):
+            a = np.moveaxis(aux.data[:g.nreal], 1, 0)
+            Q5 = parity.bubble_state(m, g, a)
+            q = omsa.MPIStateArray.from_grid(g, m.S)
+            np.moveaxis(q.data[:g.nreal], 1, 0)[...] = np.concatenate([Q5, np.stack([Q5[0] * c for c in _chi(a)])])
+            Q.append(q)
+        dQ = [q.similar() for q in Q]
+        dgm(dQ, Q, 0.0, 1, 0)
+        out = {}
+        for g, d in zip(gs, dQ):
+            c = np.round(g.vgeo[:g.nreal][:, [ogrids._x1, ogrids._x2, ogrids._x3]].mean(axis=2), 6)
+            out.update({tuple(ci): arr for ci, arr in zip(c, d.data[:g.nreal])})
+        return out
+    one, three = run(1), run(3)
+    assert one.keys() == three.keys()
+    scale = np.max([np.abs(v).max(axis=1) for v in one.values()], axis=0)[:, None]
+    for k, v in one.items():
+        assert np.max(np.abs(three[k] - v) / scale) < 1e-12
