@@ -204,3 +204,34 @@ def test_host_lsrk_tableaus_match_the_pinned_oracle():
         for h, name in zip(host, names):
             ref = [float(x) for x in oode._conv(np.float64, getattr(oode, name))]
             assert [float(x) for x in h] == ref, name
+
+
+@pytest.mark.parametrize("nranks", [4, 8])
+def test_partition_invariants_the_device_schedule_relies_on(nranks):
+    """Host-side invariants of the element partition at the rank counts of the weak-scaling runs (small
+    mesh, every rank built serially): (i) the real elements add up to the mesh, (ii) what rank r sends to a
+    neighbour is as long as what that neighbour expects from r, (iii) an *interior* element has no ghost
+    face neighbour -- the fused stepper runs the interior kernel concurrently with the halo exchange and
+    the exterior kernel, so it must not read ghost data -- and (iv) every ghost node an exterior element
+    looks at is covered by the receive map."""
+    ne, R = 6, np.array([1.0, 1.25, 1.5])
+    grids_ = [pgrids.build_grid(ptp.stacked_cubed_sphere_topology(ne, R, (1, 2), r, nranks), 4,
+                                meshwarp=ptp.cubed_sphere_warp, device="cpu") for r in range(nranks)]
+    assert sum(g.nrealelem for g in grids_) == 6 * ne * ne * 2
+    for r, g in enumerate(grids_):
+        Np = g.Np
+        for nb, (s0, s1) in zip(g.nabrtorank, g.nabrtovmapsend):
+            h = grids_[nb]
+            m = h.nabrtorank.index(r)
+            r0, r1 = h.nabrtovmaprecv[m]
+            assert s1 - s0 == r1 - r0, (r, nb)
+        vp_elem = (g.vmapP[:g.nrealelem] - 1) // Np                      # (nreal, 6, Nfp) neighbour element ids
+        inter = g.interiorelems.numpy() - 1
+        exter = g.exteriorelems.numpy() - 1
+        assert sorted(np.concatenate([inter, exter]).tolist()) == list(range(g.nrealelem))
+        assert int(vp_elem[inter].max()) < g.nrealelem                    # (iii)
+        ghost_nodes = set((g.vmaprecv - 1).tolist())
+        vp = (g.vmapP[:g.nrealelem] - 1)[exter].reshape(-1)
+        looked_at = set(vp[vp >= g.nrealelem * Np].tolist())
+        assert looked_at <= ghost_nodes                                   # (iv)
+        assert len(looked_at) > 0
