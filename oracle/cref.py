@@ -12,7 +12,13 @@ class ref_params(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("R_d", "cp_d", "cv_d", "T_0", "MSLP", "grav", "Omega")] + \
                [(n, C.c_int32) for n in ("naux", "a_Phi", "a_gradPhi", "a_ref_rho", "a_ref_p",
                                          "a_theta_v", "a_T", "subtract_off", "gravity", "coriolis",
-                                         "nf_first")] + [("bc_kind", C.c_int32 * 6)]
+                                         "nf_first")] + [("bc_kind", C.c_int32 * 6)] + \
+               [(n, C.c_int32) for n in ("second_order", "turbulence", "with_divergence",
+                                         "horizontal_diffusion", "a_Delta", "ngradflux", "held_suarez",
+                                         "sponge")] + \
+               [(n, C.c_double) for n in ("turb_param", "inv_Pr_turb", "day", "sponge_z_max",
+                                          "sponge_z_sponge", "sponge_alpha_max", "sponge_gamma")] + \
+               [("sponge_u", C.c_double * 3)]
 
 
 _lib = None
@@ -39,7 +45,9 @@ def use_all_cores():
     return n
 
 
-def params_from_model(model, nf="rusanov"):
+def params_from_model(model, nf="rusanov", second_order=False, diffusion_direction="every"):
+    """ref_params of an oracle DryAtmosModel.  `second_order`: run the gradient pass and the viscous
+    fluxes (the reference always does; False = the GPU arm's skip_zero_viscosity for nu = 0)."""
     ps = model.ps
     P = ref_params()
     P.R_d, P.cp_d, P.cv_d, P.T_0 = float(ps.R_d), float(ps.cp_d), float(ps.cv_d), float(ps.T_0)
@@ -56,6 +64,25 @@ def params_from_model(model, nf="rusanov"):
     P.nf_first = {"rusanov": 0, "central": 1}[nf]
     for i, b in enumerate(model.bcs):
         P.bc_kind[i] = 1 if b == "freeslip" else 2
+    P.second_order = int(second_order)
+    k = model.turbulence
+    P.turbulence = {"constant_kinematic": 0, "constant_dynamic": 1, "smagorinsky": 2}[k[0]]
+    P.turb_param = float(k[1])
+    P.with_divergence = int(bool(k[2])) if len(k) > 2 else 0
+    P.horizontal_diffusion = int(diffusion_direction == "horizontal")
+    P.a_Delta = -1 if model.a_Δ is None else model.a_Δ
+    P.ngradflux = model.GF
+    P.inv_Pr_turb, P.day = float(ps.inv_Pr_turb), float(ps.day)
+    P.held_suarez = int("held_suarez" in model.sources)
+    for s in model.sources:
+        if isinstance(s, tuple) and s[0] == "rayleigh_sponge":
+            P.sponge = 1
+            P.sponge_z_max, P.sponge_z_sponge, P.sponge_alpha_max = float(s[1]), float(s[2]), float(s[3])
+            for i in range(3):
+                P.sponge_u[i] = float(s[4][i])
+            P.sponge_gamma = float(s[5])
+    assert getattr(model, "hyperdiffusion", None) is None and not getattr(model, "NT", 0), \
+        "the C twin restates neither hyperdiffusion nor tracers"
     return P
 
 
@@ -66,16 +93,34 @@ def _p(a):
 class CRefDG:
     """Reference-schedule tendency / LSRK steps on one rank's oracle grid (float64, N = 4)."""
 
-    def __init__(self, model, grid, nf="rusanov"):
+    def __init__(self, model, grid, nf="rusanov", second_order=False, diffusion_direction="every"):
         assert grid.FT == np.float64 and grid.N == (4, 4, 4)
-        self.P = params_from_model(model, nf)
-        self.g = grid
-        self.D = np.ascontiguousarray(grid.D[0])
-        self.elems = np.arange(1, grid.nreal + 1, dtype=np.int64)
+        self._init(params_from_model(model, nf, second_order, diffusion_direction), grid, grid.D[0], grid.nelem)
+
+    def _init(self, P, g, D, nelem):
+        self.P, self.g = P, g
+        self.D = np.ascontiguousarray(D, dtype=np.float64)
+        self.elems = np.arange(1, g.nreal + 1, dtype=np.int64)
+        # state_gradient_flux of the twin (written by the gradient pass when P.second_order)
+        self.gradflux = np.zeros((nelem if P.second_order else 1, max(int(P.ngradflux), 1), 125))
+        for name in ("vgeo", "sgeo", "vmapM", "vmapP", "elemtobndy"):
+            a = getattr(g, name)
+            assert a.flags["C_CONTIGUOUS"] and a.dtype == (np.float64 if name in ("vgeo", "sgeo") else np.int64), name
+
+    @classmethod
+    def from_arrays(cls, P, vgeo, sgeo, vmapM, vmapP, elemtobndy, D, nreal):
+        """Twin over raw arrays in the reference layout (vgeo [nelem][25][Np], sgeo [nelem][6][Nfp][5],
+        1-based Int64 vmaps, elemtobndy [nelem][6], row-major D) with a ready ``ref_params``."""
+        import types
+        g = types.SimpleNamespace(vgeo=vgeo, sgeo=sgeo, vmapM=vmapM, vmapP=vmapP, elemtobndy=elemtobndy,
+                                  nreal=int(nreal))
+        self = cls.__new__(cls)
+        self._init(P, g, D, vgeo.shape[0])
+        return self
 
     def tendency(self, dQ, Q, aux, alpha=1.0, beta=0.0):
         g = self.g
-        lib().ref_tendency(C.byref(self.P), _p(dQ), _p(Q), _p(aux), _p(g.vgeo), _p(g.sgeo),
+        lib().ref_tendency(C.byref(self.P), _p(dQ), _p(Q), _p(aux), _p(self.gradflux), _p(g.vgeo), _p(g.sgeo),
                            _p(g.vmapM), _p(g.vmapP), _p(g.elemtobndy), _p(self.D), _p(self.elems),
                            C.c_int64(g.nreal), C.c_double(alpha), C.c_double(beta))
 
@@ -83,7 +128,7 @@ class CRefDG:
         g = self.g
         a = np.ascontiguousarray(rka, dtype=np.float64)
         b = np.ascontiguousarray(rkb, dtype=np.float64)
-        lib().ref_lsrk_steps(C.byref(self.P), _p(Q), _p(dQ), _p(aux), _p(g.vgeo), _p(g.sgeo),
+        lib().ref_lsrk_steps(C.byref(self.P), _p(Q), _p(dQ), _p(aux), _p(self.gradflux), _p(g.vgeo), _p(g.sgeo),
                              _p(g.vmapM), _p(g.vmapP), _p(g.elemtobndy), _p(self.D), _p(self.elems),
                              C.c_int64(g.nreal), C.c_double(dt), C.c_int(len(a)), _p(a), _p(b),
                              C.c_int64(nsteps))

@@ -22,55 +22,13 @@ from oracle import grids as ogrids  # noqa: E402
 
 
 def run_case(name, model, gs, Q0s, nf, dt, nsteps, rank, world, skip_zero_viscosity, diffusion_direction="every"):
-    P = parity.pkg()
-    odgm = odg.DGModel(model, gs, nf, skip_zero_viscosity=skip_zero_viscosity,
-                       diffusion_direction=diffusion_direction)
-    oQ = []
-    for g, q0 in zip(gs, Q0s):
-        q = omsa.MPIStateArray.from_grid(g, 5)
-        np.moveaxis(q.data[:g.nreal], 1, 0)[...] = q0
-        oQ.append(q)
-    g = gs[rank]
-    dgrid = parity.device_grid(g, device=f"cuda:{torch.cuda.current_device()}")
-    m = parity.device_model(model)
-    aux = P.MPIStateArray(dgrid, model.A, data=odgm.state_auxiliary[rank].data)
-    dd = P.HorizontalDirection() if diffusion_direction == "horizontal" else P.EveryDirection()
-    dg = P.DGModel(m, dgrid, getattr(P, parity.NF[nf])(), P.CentralNumericalFluxSecondOrder(),
-                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, diffusion_direction=dd,
-                   skip_zero_viscosity=skip_zero_viscosity)
-    uid = [P.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    dg.comm_init(uid[0], rank, world)
-    # ghost elements of the device state start as NaN: only the exchange may fill them
-    data = oQ[rank].data.copy()
-    data[g.nreal:] = np.nan
-    dQ = P.MPIStateArray(dgrid, 5, data=data)
-    # halo exchange known answer: ghost face nodes must equal the oracle's after exchange
-    omsa.ghost_exchange(oQ)
-    dg.ghost_exchange(dQ)
-    e, n = np.divmod(g.vmaprecv - 1, g.Np)
-    got = dQ.data.cpu().numpy()[e, :, n]
-    assert np.array_equal(got, oQ[rank].data[e, :, n]), "halo exchange mismatch"
-    # tendency
-    odQ = [q.similar() for q in oQ]
-    odgm(odQ, oQ, 0.0, 1, 0)
-    dT = P.MPIStateArray(dgrid, 5)
-    dT.data.fill_(float("nan"))
-    dg(dT, dQ, None, 0.0, 1.0, 0.0)
-    r1 = parity.rel_l2(dT.realdata.cpu().numpy(), odQ[rank].realdata)
-    # fused steps
-    osol = oode.LSRK54CarpenterKennedy(odgm, oQ, dt=dt)
-    oode.solve(oQ, osol, numberofsteps=nsteps)
-    dsol = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt)
-    P.solve(dQ, dsol, numberofsteps=nsteps)
-    r2 = parity.rel_l2(dQ.realdata.cpu().numpy(), oQ[rank].realdata)
-    res = torch.tensor([r1, r2], dtype=torch.float64, device="cuda")
-    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    res = parity.multi_rank_case(model, gs, Q0s, nf, dt, nsteps, rank, world, skip_zero_viscosity,
+                                 diffusion_direction)
     if rank == 0:
-        print(f"MULTI_GPU_PARITY {name} world={world} tendency_rel_l2={float(res[0]):.3e} "
-              f"state_rel_l2={float(res[1]):.3e}", flush=True)
-    assert float(res[0]) <= 1e-12 and float(res[1]) <= 1e-12, (name, res)
-    dg.close()
+        print(f"MULTI_GPU_PARITY {name} world={world} halo_exact={res['halo_exact']} "
+              f"tendency_rel_l2={res['tendency_rel_l2']:.3e} state_rel_l2={res['state_rel_l2']:.3e}", flush=True)
+    assert res["halo_exact"], name
+    assert res["tendency_rel_l2"] <= 1e-12 and res["state_rel_l2"] <= 1e-12, (name, res)
 
 
 def main():
@@ -101,7 +59,64 @@ def main():
            for g, a in zip(gs, tmp.state_auxiliary)]
     run_case("baroclinic_wave_hyperdiffusion", model, gs, Q0s, "rusanov", 0.5, 2, rank, world, False, "horizontal")
     run_ocean(rank, world)
+    if world == 3:
+        mpi_comm_known_answer(rank)
     dist.destroy_process_group()
+
+
+def mpi_comm_known_answer(rank):
+    """Device twin of the reference's own halo known-answer test test/Arrays/mpi_comm.jl:23-157 (three
+    ranks, hand-written vmapsend / vmaprecv / neighbour ranges, two states): the same integers go
+    through cmdg_exchange_begin / cmdg_exchange_end (pack kernel -> ncclSend/Recv -> unpack kernel).
+    The reference test uses 9 nodes per element; libcmdg is compiled for Np = 125, so node n of element
+    e of the reference's arrays is embedded as node n of element e here (linear id (e-1)*125 + n)."""
+    from tests.test_oracle_mpi_comm import RANKS
+    P = parity.pkg()
+    r = RANKS[rank]
+    Np9, Np, shift = 9, 125, 100
+    nreal, nelem = r["numreal"], r["numreal"] + r["numghost"]
+
+    def embed(ids):
+        e, n = np.divmod(np.asarray(ids, dtype=np.int64) - 1, Np9)
+        return e * Np + n + 1
+    # a grid whose real elements are isolated (every face a wall): only the halo maps matter here
+    ii = np.arange(Np).reshape((5, 5, 5), order="F")
+    fmask = np.stack([ii[0].ravel(order="F"), ii[4].ravel(order="F"), ii[:, 0].ravel(order="F"),
+                      ii[:, 4].ravel(order="F"), ii[:, :, 0].ravel(order="F"), ii[:, :, 4].ravel(order="F")])
+    vmapM = (Np * np.arange(nelem))[:, None, None] + fmask[None] + 1
+    grid = P.DiscontinuousSpectralElementGrid(
+        4, np.ones((nelem, 25, Np)), np.ones((nelem, 6, 25, 5)), vmapM, vmapM, np.ones((nelem, 6), dtype=np.int64),
+        np.eye(5), nreal, interiorelems=np.zeros(0, dtype=np.int64), exteriorelems=np.arange(1, nreal + 1),
+        vmapsend=embed(r["vmapsend"]), vmaprecv=embed(r["vmaprecv"]), nabrtorank=r["nabrtorank"],
+        nabrtovmapsend=r["nabrtovmapsend"], nabrtovmaprecv=r["nabrtovmaprecv"],
+        device=f"cuda:{torch.cuda.current_device()}")
+    model = P.AtmosModel(boundaryconditions=(P.AtmosBC(),))
+    dg = P.DGModel(model, grid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), skip_zero_viscosity=True)
+    uid = [P.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    dg.comm_init(uid[0], rank, 3)
+    data = np.full((nelem, 2, Np), -1.0)
+    vals = rank * 1000 + np.arange(1, Np9 * nreal + 1).reshape(nreal, Np9)
+    data[:nreal, 0, :Np9] = vals
+    data[:nreal, 1, :Np9] = vals + shift
+    A = P.MPIStateArray(grid, 2, data=data)
+    dg.ghost_exchange(A)
+    got = A.data.cpu().numpy()
+    e, n = np.divmod(np.asarray(r["vmaprecv"]) - 1, Np9)
+    ok = np.array_equal(got[e, 0, n], np.asarray(r["expected"], dtype=np.float64)) and \
+        np.array_equal(got[e, 1, n], shift + np.asarray(r["expected"], dtype=np.float64))
+    # only the listed ghost nodes were written
+    untouched = np.ones((nelem, Np), dtype=bool)
+    untouched[:nreal, :Np9] = False
+    untouched[e, n] = False
+    ok = ok and bool(np.all(got[:, 0][untouched] == -1.0))
+    flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY mpi_comm_known_answer world=3 exact={float(flag) == 0.0}", flush=True)
+    assert float(flag) == 0.0, "mpi_comm.jl known answers not reproduced by the device halo exchange"
+    dg.close()
 
 
 def run_ocean(rank, world):

@@ -130,6 +130,77 @@ def compare_case(model, g, Q0, nf="rusanov", nsteps=1, dt=None, diffusion_direct
     return res
 
 
+def multi_rank_case(model, gs, Q0s, nf, dt, nsteps, rank, world, skip_zero_viscosity,
+                    diffusion_direction="every", device=None):
+    """One rank's share of a `world`-rank run (torch.distributed initialised by the caller when
+    world > 1): the oracle emulates all ranks serially (Hilbert partition, ghost lists, halo
+    exchange); this rank runs libcmdg on its partition with the NCCL halo exchange.  Returns the
+    maxima over ranks of
+      halo_exact        ghost face nodes after cmdg_exchange_begin/end == the oracle's (array_equal;
+                        ghosts start as NaN, so only the exchange can have filled them),
+      tendency_rel_l2   one cmdg_tendency (reference order: interior while the halo is in flight),
+      state_rel_l2      `nsteps` fused LSRK54 steps (cmdg_lsrk_steps: exterior-first / overlapped).
+    """
+    import torch
+    import torch.distributed as dist
+    P = pkg()
+    odgm = odg.DGModel(model, gs, nf, skip_zero_viscosity=skip_zero_viscosity,
+                       diffusion_direction=diffusion_direction)
+    oQ = []
+    for g, q0 in zip(gs, Q0s):
+        q = omsa.MPIStateArray.from_grid(g, 5)
+        np.moveaxis(q.data[:g.nreal], 1, 0)[...] = q0
+        oQ.append(q)
+    g = gs[rank]
+    device = device or f"cuda:{torch.cuda.current_device()}"
+    dgrid = device_grid(g, device=device)
+    m = device_model(model)
+    aux = P.MPIStateArray(dgrid, model.A, data=odgm.state_auxiliary[rank].data)
+    dd = P.HorizontalDirection() if diffusion_direction == "horizontal" else P.EveryDirection()
+    dg = P.DGModel(m, dgrid, getattr(P, NF[nf])(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, diffusion_direction=dd,
+                   skip_zero_viscosity=skip_zero_viscosity)
+    if world > 1:
+        uid = [P.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dg.comm_init(uid[0], rank, world)
+    # ghost elements of the device state start as NaN: only the exchange may fill them
+    data = oQ[rank].data.copy()
+    data[g.nreal:] = np.nan
+    dQ = P.MPIStateArray(dgrid, 5, data=data)
+    # halo exchange known answer: ghost face nodes must equal the oracle's after exchange
+    omsa.ghost_exchange(oQ)
+    halo_exact = True
+    if world > 1:
+        dg.ghost_exchange(dQ)
+        e, n = np.divmod(g.vmaprecv - 1, g.Np)
+        got = dQ.data.cpu().numpy()[e, :, n]
+        halo_exact = bool(np.array_equal(got, oQ[rank].data[e, :, n]))
+    # tendency
+    odQ = [q.similar() for q in oQ]
+    odgm(odQ, oQ, 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 5)
+    dT.data.fill_(float("nan"))
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    r1 = rel_l2(dT.realdata.cpu().numpy(), odQ[rank].realdata)
+    # fused steps
+    osol = oode.LSRK54CarpenterKennedy(odgm, oQ, dt=dt)
+    oode.solve(oQ, osol, numberofsteps=nsteps)
+    dsol = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt)
+    P.solve(dQ, dsol, numberofsteps=nsteps)
+    r2 = rel_l2(dQ.realdata.cpu().numpy(), oQ[rank].realdata)
+    res = torch.tensor([r1, r2, 0.0 if halo_exact else 1.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    out = {"n_ranks": world, "halo_exact": float(res[2]) == 0.0, "tendency_rel_l2": float(res[0]),
+           "state_rel_l2": float(res[1]), "nsteps": nsteps,
+           "nreal_per_rank": [int(x.nreal) for x in gs], "ninterior_per_rank": [int(len(x.interiorelems)) for x in gs],
+           "nghost_per_rank": [int(x.nelem - x.nreal) for x in gs],
+           "nneighbours_per_rank": [int(len(x.nabrtorank)) for x in gs]}
+    dg.close()
+    return out
+
+
 def vortex_setup(nelem=(5, 5, 1), FT=np.float64, csize=1):
     ps = oatmos.Params(FT)
     setup = oatmos.IsentropicVortexSetup(ps, FT)

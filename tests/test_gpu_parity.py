@@ -231,22 +231,26 @@ def test_courant_numbers():
         assert abs(got - ref) <= 1e-12 * ref, (key, got, ref)
 
 
-def test_multi_gpu_halo_and_parity():
-    """2 ranks over NCCL (needs >= 2 GPUs; the 1-GPU box skips it, `gpurun --gpus 2` runs it)."""
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_multi_gpu_halo_and_parity(world):
+    """`world` ranks over NCCL (needs that many GPUs: `gpurun --gpus 2|4|8` runs them, a smaller box
+    skips; bench.py carries the same check in its `parity` key at every --gpus N so the driver's
+    scaling run sees it).  world = 3 also runs the device twin of the reference's halo known-answer
+    test test/Arrays/mpi_comm.jl:23-157."""
     import os
     import subprocess
     import sys
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run(
-        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-         "--master-addr", "127.0.0.1", "--master-port", "29511",
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+         "--master-addr", "127.0.0.1", "--master-port", str(29511 + world),
          os.path.join(root, "tests", "multi_gpu_parity.py")],
-        capture_output=True, text=True, timeout=900)
+        capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MULTI_GPU_PARITY") == 5
+    assert out.stdout.count("MULTI_GPU_PARITY") == (6 if world == 3 else 5)
 
 
 def test_ocean_hbmodel_tendency_and_steps():
