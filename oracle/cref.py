@@ -22,6 +22,21 @@ class ref_params(C.Structure):
 
 
 _lib = None
+_lib_ld = None
+_SO_LD = os.path.join(_HERE, "c", "libdgref_ld.so")
+
+
+def lib_ld():
+    """The same C code built in x87 extended precision (`real` = long double; 64-bit mantissa)."""
+    global _lib_ld
+    if _lib_ld is None:
+        if not os.path.exists(_SO_LD):
+            raise RuntimeError(f"{_SO_LD} missing: run `make -C oracle/c`")
+        _lib_ld = C.CDLL(_SO_LD)
+        _lib_ld.ref_real_bytes.restype = C.c_int
+        assert _lib_ld.ref_real_bytes() == np.dtype(np.longdouble).itemsize == 16, "x86-64 long double expected"
+        _lib_ld.ref_set_num_threads.argtypes = [C.c_int]
+    return _lib_ld
 
 
 def lib():
@@ -117,6 +132,27 @@ class CRefDG:
         self = cls.__new__(cls)
         self._init(P, g, D, vgeo.shape[0])
         return self
+
+    def tendency_extended(self, Q, aux):
+        """One evaluation (alpha = 1, beta = 0) of the same schedule in extended precision on the same
+        Float64 inputs; returns the tendency as np.longdouble (nelem, 5, Np).  The yardstick for
+        ill-conditioned states: how far is a Float64 evaluation from the exactly rounded one?"""
+        L = lib_ld()
+        try:
+            L.ref_set_num_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            pass
+        g = self.g
+        ld = lambda a: np.ascontiguousarray(a, dtype=np.longdouble)
+        if not hasattr(self, "_ld"):
+            self._ld = dict(vgeo=ld(g.vgeo), sgeo=ld(g.sgeo), D=ld(self.D))
+        x = self._ld
+        Ql, al, gl = ld(Q), ld(aux), ld(self.gradflux)
+        dQ = np.zeros_like(Ql)
+        L.ref_tendency(C.byref(self.P), _p(dQ), _p(Ql), _p(al), _p(gl), _p(x["vgeo"]), _p(x["sgeo"]),
+                       _p(g.vmapM), _p(g.vmapP), _p(g.elemtobndy), _p(x["D"]), _p(self.elems),
+                       C.c_int64(g.nreal), C.c_longdouble(1.0), C.c_longdouble(0.0))
+        return dQ
 
     def tendency(self, dQ, Q, aux, alpha=1.0, beta=0.0):
         g = self.g
