@@ -273,3 +273,57 @@ def test_ocean_gyre_reference_values_on_device():
         digs = DIGITS.get(key, (12, 12, 12, 12))
         for gval, r, d in zip(got[key], ref, digs):
             assert close_digits(gval, r, d - 2), (key, got[key], ref)
+
+
+def test_plain_c_abi_driver(tmp_path):
+    """A non-Python process drives libcmdg.so through the C ABI: tests/abi_driver.c (plain C, dlopen +
+    dlsym, cudaMalloc'ed arrays in the reference layouts) runs create / bind_grid / bind_state / tendency /
+    lsrk_steps / destroy on raw arrays the oracle dumped, and compares with the oracle's own tendency and
+    state after two LSRK54 steps (dry baroclinic wave on the cubed sphere, pushed 1 % off balance)."""
+    import os
+    import subprocess
+    from oracle import dgmodel as odg, atmos as oatmos, odesolvers as oode, mpistatearrays as omsa
+    from tests import bench_checks
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drv, lib = os.path.join(root, "tests", "abi_driver"), os.path.join(root, "climatemachine.jl_b200", "libcmdg.so")
+    assert os.path.exists(drv), "tests/abi_driver missing: run __graft_entry__.build()"
+    model, gs = parity.gcm_setup(3, 2)
+    g = gs[0]
+    dgm = odg.DGModel(model, [g], "rusanov", skip_zero_viscosity=True)
+    A = np.moveaxis(dgm.state_auxiliary[0].data[:g.nreal], 1, 0)
+    q0 = oatmos.init_baroclinic_wave(model, A)
+    pert, du, dw = bench_checks.unbalance(q0, A[0:3], np)
+    q0 = q0 * pert
+    q0[1] += du * q0[0]
+    q0[3] += dw * q0[0]
+    q = omsa.MPIStateArray.from_grid(g, 5)
+    np.moveaxis(q.data[:g.nreal], 1, 0)[...] = q0
+    d = str(tmp_path)
+    dump = lambda name, a, dt: np.ascontiguousarray(a, dtype=dt).tofile(os.path.join(d, name))
+    dump("vgeo.bin", g.vgeo, np.float64)
+    dump("sgeo.bin", g.sgeo, np.float64)
+    dump("vmapM.bin", g.vmapM, np.int64)
+    dump("vmapP.bin", g.vmapP, np.int64)
+    dump("elemtobndy.bin", g.elemtobndy, np.int64)
+    dump("D.bin", g.D[0].T, np.float64)                 # Julia (column-major) memory order
+    dump("Q.bin", q.data, np.float64)
+    dump("aux.bin", dgm.state_auxiliary[0].data, np.float64)
+    dq = q.similar()
+    dgm([dq], [q], 0.0, 1, 0)
+    dump("expect_tendency.bin", dq.realdata, np.float64)
+    nsteps, dt = 2, 0.5
+    sol = oode.LSRK54CarpenterKennedy(dgm, [q], dt=dt)
+    oode.solve([q], sol, numberofsteps=nsteps)
+    dump("expect_state.bin", q.realdata, np.float64)
+    ps = model.ps
+    meta = dict(nelem=g.nelem, nrealelem=g.nreal, nvertelem=g.topology.stacksize, nstate=5, naux=model.A,
+                ngrad=model.G, ngradflux=model.GF, nf_first=0, orientation=2, ref_state=1, subtract_off=1,
+                turbulence=0, turb_param=0.0, sources=3, diffusion_direction=0, skip_zero_viscosity=1, nbc=2,
+                R_d=ps.R_d, cp_d=ps.cp_d, cv_d=ps.cv_d, T_0=ps.T_0, MSLP=ps.MSLP, grav=ps.grav, Omega=ps.Omega,
+                inv_Pr_turb=ps.inv_Pr_turb, day=ps.day, dt=dt, nsteps=nsteps)
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        for k, v in meta.items():
+            f.write(f"{k} {float(v)!r}\n")
+    out = subprocess.run([drv, lib, d], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ABI_DRIVER tendency_rel_l2=" in out.stdout, out.stdout
