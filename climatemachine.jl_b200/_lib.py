@@ -118,10 +118,9 @@ def lib():
     L.cmdg_last_kernel_ms.restype = dbl
     L.cmdg_kernel_class_ms.argtypes = [vp, i32, C.POINTER(i64)]
     L.cmdg_kernel_class_ms.restype = dbl
-    for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("cmdg_version",):
-            pass
+    missing = [name for name in SYMBOLS if not hasattr(L, name)]
+    if missing:
+        raise CmdgError(f"{LIB_PATH} does not export {missing} (stale build?)")
     _lib = L
     return L
 

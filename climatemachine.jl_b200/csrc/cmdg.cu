@@ -74,6 +74,7 @@ struct cmdg_handle_s {
   cmdg_desc d{};
   std::string err;
   int Nq = 0, Np = 0, Nfp = 0;
+  int device = 0; // CUDA device current at cmdg_create (the handle's GPU)
   size_t fb = 8;  // bytes per float
   bool aux_model = false, visc = false;
   int pf_dist = 296;      // L2 prefetch distance of the one-shot tendency kernel: 2 blocks per SM ahead (CMDG_PF overrides)
@@ -138,7 +139,19 @@ struct cmdg_handle_s {
   std::vector<int> tev_class;
   double class_ms[CMDG_KCLASS_COUNT] = {0};
   int64_t class_n[CMDG_KCLASS_COUNT] = {0};
+  // per-stage timeline of the last two steps of a cmdg_lsrk_steps call (diagnostic; CMDG_TIMELINE=<path>
+  // with timing enabled): labelled marks recorded on the stream that does the work, dumped as CSV
+  struct TlMark { cudaEvent_t ev; int label; long long info; int step, stage; };
+  std::vector<TlMark> tl;
+  size_t tl_used = 0;
+  std::string tl_path;
+  bool tl_on = false;
+  int tl_step = 0, tl_stage = 0;
 };
+enum { TL_STEP_BEGIN = 0, TL_KERNEL_BEGIN, TL_KERNEL_END, TL_PACK_END, TL_NCCL_BEGIN, TL_NCCL_END,
+       TL_UNPACK_BEGIN, TL_UNPACK_END, TL_COUNT };
+static const char *const TL_NAMES[TL_COUNT] = {"step_begin", "kernel_begin", "kernel_end", "pack_end", "nccl_begin",
+                                               "nccl_end", "unpack_begin", "unpack_end"};
 
 namespace {
 
@@ -233,11 +246,44 @@ cudaEvent_t timing_event(cmdg_handle h, int kclass = CMDG_KCLASS_TENDENCY) {
   return h->tev[h->tev_used++];
 }
 
+void tl_mark(cmdg_handle h, cudaStream_t st, int label, long long info = 0) {
+  if (!h->tl_on) return;
+  if (h->tl_used == h->tl.size()) {
+    cmdg_handle_s::TlMark m{};
+    cudaEventCreate(&m.ev);
+    h->tl.push_back(m);
+  }
+  cmdg_handle_s::TlMark &m = h->tl[h->tl_used++];
+  m.label = label;
+  m.info = info;
+  m.step = h->tl_step;
+  m.stage = h->tl_stage;
+  cudaEventRecord(m.ev, st);
+}
+
+void tl_dump(cmdg_handle h) {
+  if (h->tl_path.empty() || h->tl_used == 0) return;
+  const std::string path = h->tl_path + ".rank" + std::to_string(h->rank) + ".csv";
+  FILE *f = fopen(path.c_str(), "w");
+  if (!f) return;
+  fprintf(f, "step,stage,label,info,t_us\n");
+  cudaEvent_t t0 = h->tl[0].ev;
+  for (size_t i = 0; i < h->tl_used; ++i) {
+    const cmdg_handle_s::TlMark &m = h->tl[i];
+    if (m.label == TL_STEP_BEGIN) t0 = m.ev;
+    float x = 0;
+    cudaEventElapsedTime(&x, t0, m.ev);
+    fprintf(f, "%d,%d,%s,%lld,%.3f\n", m.step, m.stage, TL_NAMES[m.label], m.info, 1e3 * (double)x);
+  }
+  fclose(f);
+}
+
 // The constant-memory copy of D is per process: re-upload when another handle used it last.
 const cmdg_handle_s *g_constD_owner = nullptr;
+int g_constD_device = -1;
 template <class R>
 int ensure_const_D(cmdg_handle h, cudaStream_t st) {
-  if (g_constD_owner == h) return 0;
+  if (g_constD_owner == h && g_constD_device == h->device) return 0;
   if (sizeof(R) == 8) {
     CU(cudaMemcpyToSymbolAsync(c_D64, h->Dhost.data(), 64 * sizeof(double), 0, cudaMemcpyHostToDevice, st));
   } else {
@@ -247,6 +293,7 @@ int ensure_const_D(cmdg_handle h, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));
   }
   g_constD_owner = h;
+  g_constD_device = h->device;
   return 0;
 }
 
@@ -256,13 +303,16 @@ int launch_tend_inst(cmdg_handle h, const TendArgs<R> &a, const AtmosParams<R> &
   using SM = TendSmem<R, NQ, AUX, VISC>;
   if (int rc = ensure_const_D<R>(h, st)) return rc;
   auto kern = dg_tendency_kernel<R, NQ, NF1, AUX, VISC, SRCX>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per device (a process may hold handles on several GPUs): once per device and instantiation
+  static unsigned long long attr_devices = 0;   // bit d: attribute set on device d for this instantiation
+  if (h->device >= 64 || !((attr_devices >> h->device) & 1ull)) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    attr_set = true;
+    if (h->device < 64) attr_devices |= 1ull << h->device;
   }
   if (h->timing) cudaEventRecord(timing_event(h), st);
+  tl_mark(h, st, TL_KERNEL_BEGIN, (long long)n);
   kern<<<(unsigned)n, Dims<NQ>::BLOCK, sizeof(SM), st>>>(a, P);
+  tl_mark(h, st, TL_KERNEL_END, (long long)n);
   if (h->timing) cudaEventRecord(timing_event(h), st);
   CU(cudaGetLastError());
   h->launches++;
@@ -301,10 +351,10 @@ int launch_gradient_inst(cmdg_handle h, const GradArgs<R> &a, const AtmosParams<
                          cudaStream_t st) {
   using SM = GradSmem<R, 5, AUX, HYPER>;
   auto kern = dg_gradient_kernel<R, 5, AUX, HYPER>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devices = 0;
+  if (h->device >= 64 || !((attr_devices >> h->device) & 1ull)) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    attr_set = true;
+    if (h->device < 64) attr_devices |= 1ull << h->device;
   }
   if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
   kern<<<(unsigned)n, Dims<5>::BLOCK, sizeof(SM), st>>>(a, P);
@@ -458,8 +508,10 @@ int exchange_begin_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
     CU(cudaGetLastError());
     h->launches++;
   }
+  tl_mark(h, st, TL_PACK_END, (long long)h->nvmapsend * nstate);
   CU(cudaEventRecord(h->ev_ready, st));
   CU(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  tl_mark(h, h->comm_stream, TL_NCCL_BEGIN);
   NC(g_nccl.GroupStart());
   for (size_t n = 0; n < h->nabrtorank.size(); ++n) {
     const int64_t r0 = h->recvrange[2 * n], r1 = h->recvrange[2 * n + 1];
@@ -472,6 +524,7 @@ int exchange_begin_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
                    h->comm_stream));
   }
   NC(g_nccl.GroupEnd());
+  tl_mark(h, h->comm_stream, TL_NCCL_END);
   CU(cudaEventRecord(h->ev_done, h->comm_stream));
   h->exchange_open = true;
   return 0;
@@ -483,12 +536,14 @@ int exchange_end_t(cmdg_handle h, void *array, int nstate, cudaStream_t st) {
   if (!h->exchange_open)
     return fail(h, CMDG_ERR_INVALID, "A ghost exchange must begin before it ends.");
   CU(cudaStreamWaitEvent(st, h->ev_done, 0));
+  tl_mark(h, st, TL_UNPACK_BEGIN);
   if (h->nvmaprecv > 0) {
     unpack_kernel<R><<<(unsigned)((h->nvmaprecv + 255) / 256), 256, 0, st>>>(
         (R *)array, (const R *)h->recvbuf, h->vmaprecv0, h->nvmaprecv, h->Np, nstate);
     CU(cudaGetLastError());
     h->launches++;
   }
+  tl_mark(h, st, TL_UNPACK_END);
   h->exchange_open = false;
   return 0;
 }
@@ -739,7 +794,7 @@ int lsrk_update_t(cmdg_handle h, void *dQ, void *Q, double rka, double rkb, doub
 // Filters.apply! on real elements; Wh / Wv are row-major device matrices
 template <class R>
 int filter_apply_t(cmdg_handle h, void *Q, int nstate, int target, unsigned mask, const void *Wh,
-                   const void *Wv, int direction, cudaStream_t st) {
+                   const void *Wv, int direction, cudaStream_t st, int julia_layout = 0) {
   const int64_t nreal = h->d.nrealelem;
   if (nreal <= 0) return 0;
   int a_rho = 0, a_rhoe = 0;
@@ -755,7 +810,7 @@ int filter_apply_t(cmdg_handle h, void *Q, int nstate, int target, unsigned mask
   if (nstate <= 5)
     filter_kernel<R, 5, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(
         (R *)Q, (const R *)h->aux, (const R *)Wh, (const R *)Wv, nstate, h->d.naux, mask, target, a_rho,
-        a_rhoe, do_h, do_v);
+        a_rhoe, do_h, do_v, julia_layout);
   else
     return fail(h, CMDG_ERR_UNSUPPORTED, "filter: at most 5 states");
   CU(cudaGetLastError());
@@ -803,9 +858,15 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
     CU(cudaEventRecord(h->ev_int, st));
     CU(cudaStreamWaitEvent(xs, h->ev_int, 0));
   }
+  h->tl_used = 0;
   for (int64_t step = 0; step < nsteps; ++step) {
     const double time = t0 + (double)step * dt;
+    h->tl_on = h->timing && !h->tl_path.empty() && step + 2 >= nsteps;
+    h->tl_step = (int)step;
+    h->tl_stage = 0;
+    tl_mark(h, st, TL_STEP_BEGIN);
     for (int s = 0; s < nstage; ++s) {
+      h->tl_stage = s;
       if (h->is_hb) {
         int rc = hb_eval_t<R>(h, dQ, cur, nxt, 1.0, rka[s], (double)((R)rkb[s] * (R)dt), st);
         if (rc) return rc;
@@ -891,6 +952,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       }
     }
   }
+  h->tl_on = false;
   if (cur != (R *)Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
   // the reference leaves dQ scaled by RKA[1] after the last stage (:130-141)
   const size_t n = (size_t)nreal * h->d.nstate * h->Np;
@@ -916,6 +978,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
     }
     h->last_ms = ms;
     h->last_nl = nl;
+    tl_dump(h);
   }
   return 0;
 }
@@ -1080,6 +1143,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
     if (cudaGetDeviceCount(&ndev0) != cudaSuccess || ndev0 == 0)
       return fail(nullptr, CMDG_ERR_NODEVICE, "no CUDA device available (libcmdg has no CPU fallback)");
     h = new cmdg_handle_s();
+    cudaGetDevice(&h->device);
     h->d = *d;
     h->Nq = d->N + 1;
     h->Np = h->Nq * h->Nq * h->Nq;
@@ -1087,6 +1151,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
     h->fb = d->float_bytes;
     h->is_hb = true;
     h->visc = true;
+    if (const char *kv = getenv("CMDG_TIMELINE")) h->tl_path = kv;
     if (cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
@@ -1151,6 +1216,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CMDG_ERR_NODEVICE, "no CUDA device available (libcmdg has no CPU fallback)");
   h = new cmdg_handle_s();
+  cudaGetDevice(&h->device);
   h->d = *d;
   h->Nq = d->N + 1;
   h->Np = h->Nq * h->Nq * h->Nq;
@@ -1162,6 +1228,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   h->hyper = hyp;
   h->ntracers = nt;
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
+  if (const char *kv = getenv("CMDG_TIMELINE")) h->tl_path = kv;
   if (const char *kv = getenv("CMDG_OVERLAP")) h->overlap_exterior = atoi(kv) != 0;
   // the NCCL send/recv kernel is launched while the interior kernel still has thousands of blocks
   // queued: on a stream of the same priority its CTAs would be dispatched after them, i.e. the halo
@@ -1195,6 +1262,7 @@ int cmdg_destroy(cmdg_handle h) {
   for (void *p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  for (auto &m : h->tl) cudaEventDestroy(m.ev);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ext_stream) cudaStreamDestroy(h->ext_stream);
@@ -1337,6 +1405,7 @@ int cmdg_tendency(cmdg_handle h, void *dQ, void *Q, double t, double alpha, doub
   if (rc) return rc;
   if (!dQ || !Q) return fail(h, CMDG_ERR_INVALID, "null state array");
   cudaStream_t st = (cudaStream_t)stream;
+  h->tev_used = 0;   // per-launch timing events are only evaluated by cmdg_lsrk_steps: reuse the pool here
   return DISPATCH_FT(h, tendency_t<double>(h, dQ, Q, t, alpha, beta, st),
                      tendency_t<float>(h, dQ, Q, t, alpha, beta, st));
 }
@@ -1394,16 +1463,11 @@ int cmdg_filter_apply(cmdg_handle h, void *Q, int32_t nstate, int32_t target, ui
   if (direction < CMDG_DIR_EVERY || direction > CMDG_DIR_VERTICAL)
     return fail(h, CMDG_ERR_INVALID, "bad filter direction");
   if (nstate < 1 || nstate > 5) return fail(h, CMDG_ERR_UNSUPPORTED, "filter: 1..5 states");
-  // matrices arrive in Julia layout: transpose into scratch copies
-  int rc;
-  if (h->fb == 8) {
-    if ((rc = transpose_small<double>(h, filter_h, h->Nq, &h->tmpWh))) return rc;
-    if ((rc = transpose_small<double>(h, filter_v, h->Nq, &h->tmpWv))) return rc;
-    return filter_apply_t<double>(h, Q, nstate, target, state_mask, h->tmpWh, h->tmpWv, direction, (cudaStream_t)stream);
-  }
-  if ((rc = transpose_small<float>(h, filter_h, h->Nq, &h->tmpWh))) return rc;
-  if ((rc = transpose_small<float>(h, filter_v, h->Nq, &h->tmpWv))) return rc;
-  return filter_apply_t<float>(h, Q, nstate, target, state_mask, h->tmpWh, h->tmpWv, direction, (cudaStream_t)stream);
+  // the matrices are read in the caller's Julia layout by the kernel itself: no scratch copy, no host
+  // round trip, fully asynchronous on the caller's stream
+  if (h->fb == 8)
+    return filter_apply_t<double>(h, Q, nstate, target, state_mask, filter_h, filter_v, direction, (cudaStream_t)stream, 1);
+  return filter_apply_t<float>(h, Q, nstate, target, state_mask, filter_h, filter_v, direction, (cudaStream_t)stream, 1);
 }
 
 int cmdg_set_step_filter(cmdg_handle h, int32_t target, uint32_t state_mask, const void *filter_h,
@@ -1497,6 +1561,16 @@ int cmdg_comm_init(cmdg_handle h, const void *id128, int32_t rank, int32_t nrank
   NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
   h->rank = rank;
   h->nranks = nranks;
+  // halo buffers for the widest array the library itself exchanges (Q, F2 / Qhg: 12, HB gradient flux: 10,
+  // tracer fluxes) or the harness may (state_auxiliary): no cudaFree / cudaMalloc in the middle of a step
+  if (!h->nabrtorank.empty()) {
+    size_t ns = std::max<size_t>((size_t)h->d.nstate, (size_t)h->d.naux);
+    ns = std::max<size_t>(ns, 12);
+    ns = std::max<size_t>(ns, (size_t)(3 * h->d.ntracers));
+    CU(cudaMalloc(&h->sendbuf, (size_t)h->nvmapsend * ns * h->fb + 16));
+    CU(cudaMalloc(&h->recvbuf, (size_t)h->nvmaprecv * ns * h->fb + 16));
+    h->commbuf_states = ns;
+  }
   return CMDG_OK;
 }
 

@@ -931,14 +931,16 @@ template <class R, int NQ, int MAXS>
 __global__ void __launch_bounds__(Dims<NQ>::BLOCK)
 filter_kernel(R *__restrict__ Q, const R *__restrict__ aux, const R *__restrict__ Wh,
               const R *__restrict__ Wv, int nstate, int naux, unsigned mask, int target,
-              int a_ref_rho, int a_ref_rhoe, int do_h, int do_v) {
+              int a_ref_rho, int a_ref_rhoe, int do_h, int do_v, int julia_layout) {
   constexpr int NP = Dims<NQ>::NP;
   __shared__ R s[MAXS][NP];
   __shared__ R sW[2][NQ * NQ];
   const int tid = threadIdx.x, e = blockIdx.x;
   if (tid < NQ * NQ) {
-    sW[0][tid] = Wh[tid];
-    sW[1][tid] = Wv[tid];
+    // row-major W[r][c] at r * Nq + c; the caller's Julia (column-major) matrix has it at r + Nq * c
+    const int src = julia_layout ? (tid / NQ) + NQ * (tid % NQ) : tid;
+    sW[0][tid] = Wh[src];
+    sW[1][tid] = Wv[src];
   }
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   R v[MAXS], ref[MAXS];

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Per-stage table of the CMDG_TIMELINE dumps (one CSV per rank; libcmdg records labelled CUDA events on
+the stream that does the work during the last two steps of a timed cmdg_lsrk_steps call).
+
+    CMDG_TIMELINE=gpurun_out/tl python -m torch.distributed.run ... bench.py --gpus N --headline-only
+    python tools/timeline_table.py gpurun_out/tl > profiles/r2_timeline_nN.md
+
+Columns (microseconds, last recorded step): for every stage the exterior chain on the side stream
+(exterior kernel, pack, wait for NCCL to start, NCCL send/recv, unpack) next to the interior kernel on
+the main stream, what the stage cost (from its first kernel start to the last of both chains) and how
+much of that the exterior chain stuck out beyond the interior kernel ("exposed")."""
+import csv
+import glob
+import sys
+from collections import defaultdict
+
+
+def load(path):
+    rows = list(csv.DictReader(open(path)))
+    steps = sorted({int(r["step"]) for r in rows})
+    last = steps[-1]
+    by_stage = defaultdict(list)
+    for r in rows:
+        if int(r["step"]) == last:
+            by_stage[int(r["stage"])].append((r["label"], int(r["info"]), float(r["t_us"])))
+    return by_stage
+
+
+def stage_row(marks):
+    kb = [(i, t) for (l, i, t) in marks if l == "kernel_begin"]
+    ke = [(i, t) for (l, i, t) in marks if l == "kernel_end"]
+    get = lambda name: [t for (l, i, t) in marks if l == name]
+    if len(kb) < 2:      # serial schedule or single rank
+        return None
+    # exterior launch = the smaller one
+    (ie, te0), (ii, ti0) = sorted(kb)[0], sorted(kb)[-1]
+    te1 = [t for (i, t) in ke if i == ie][0]
+    ti1 = [t for (i, t) in ke if i == ii][0]
+    pack, nb, ne_, ub, ue = get("pack_end")[0], get("nccl_begin")[0], get("nccl_end")[0], get("unpack_begin")[0], get("unpack_end")[0]
+    start = min(te0, ti0)
+    end = max(ue, ti1)
+    return dict(ext_kernel=te1 - te0, pack=pack - te1, nccl_wait=nb - pack, nccl=ne_ - nb, unpack_wait=ub - ne_,
+                unpack=ue - ub, ext_chain=ue - te0, interior=ti1 - ti0, int_start_after_ext=ti0 - te0,
+                stage=end - start, exposed=max(0.0, ue - ti1), start=start, end=end, n_ext=ie, n_int=ii)
+
+
+def main():
+    prefix = sys.argv[1]
+    files = sorted(glob.glob(prefix + ".rank*.csv"))
+    print(f"# Stage timeline, {len(files)} rank(s), last recorded step (microseconds)\n")
+    cols = ["ext_kernel", "pack", "nccl_wait", "nccl", "unpack_wait", "unpack", "ext_chain", "interior",
+            "int_start_after_ext", "stage", "exposed", "gap_to_next"]
+    summary = []
+    for f in files:
+        rank = f.split(".rank")[-1].split(".")[0]
+        st = load(f)
+        rows = [stage_row(st[s]) for s in sorted(st)]
+        if any(r is None for r in rows):
+            print(f"rank {rank}: serial schedule / single rank (no exterior chain recorded)\n")
+            continue
+        for a, b in zip(rows, rows[1:]):
+            a["gap_to_next"] = b["start"] - a["end"]
+        rows[-1]["gap_to_next"] = float("nan")
+        print(f"## rank {rank}  (exterior {rows[0]['n_ext']} / interior {rows[0]['n_int']} elements)\n")
+        print("| stage | " + " | ".join(cols) + " |")
+        print("|---|" + "---|" * len(cols))
+        for s, r in enumerate(rows):
+            print(f"| {s + 1} | " + " | ".join(f"{r[c]:.1f}" for c in cols) + " |")
+        tot = {c: sum(r[c] for r in rows if r[c] == r[c]) for c in cols}
+        print("| sum | " + " | ".join(f"{tot[c]:.1f}" for c in cols) + " |\n")
+        summary.append((rank, tot))
+    if summary:
+        print("## per-rank sums over the 5 stages\n")
+        print("| rank | interior | ext_chain | exposed | gaps | stage total |")
+        print("|---|---|---|---|---|---|")
+        for rank, t in summary:
+            print(f"| {rank} | {t['interior']:.1f} | {t['ext_chain']:.1f} | {t['exposed']:.1f} | {t['gap_to_next']:.1f} | {t['stage']:.1f} |")
+
+
+if __name__ == "__main__":
+    main()
