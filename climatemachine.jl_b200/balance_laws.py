@@ -344,6 +344,21 @@ class OceanGyre:
                                   OceanBC(Penetrable(KinematicStress()), TemperatureFlux()))
 
 
+@dataclass(frozen=True)
+class HomogeneousBox:
+    """``HomogeneousBox`` (src/Ocean/OceanProblems/homogeneous_box.jl:15-66): jet-like wind stress, constant
+    temperature; no temperature relaxation (lambda_r = theta_E = 0 in the descriptor)."""
+    Lˣ: float
+    Lʸ: float
+    H: float
+    τₒ: float = 1e-1
+    boundary_conditions: Tuple = (OceanBC(Impenetrable(NoSlip()), Insulating()),
+                                  OceanBC(Impenetrable(NoSlip()), Insulating()),
+                                  OceanBC(Penetrable(KinematicStress()), Insulating()))
+    λʳ: float = 0.0
+    θᴱ: float = 0.0
+
+
 @dataclass
 class HydrostaticBoussinesqModel:
     problem: OceanGyre
@@ -370,8 +385,8 @@ class HydrostaticBoussinesqModel:
         for name in ("momentum_advection", "coupling", "forcing"):
             if getattr(self, name) is not None:
                 raise UnsupportedModelError(f"HBModel.{name} is not supported by libcmdg")
-        if not isinstance(self.problem, OceanGyre):
-            raise UnsupportedModelError("only OceanGyre-type problems are supported")
+        if not isinstance(self.problem, (OceanGyre, HomogeneousBox)):
+            raise UnsupportedModelError("only OceanGyre / HomogeneousBox problems are supported")
         for bc in self.problem.boundary_conditions:
             ocean_bc_codes(bc)
 

@@ -239,7 +239,8 @@ def float32_truth_errors(model, g, Q0, nf, skip_zero_viscosity, diffusion_direct
     g64.vgeo, g64.sgeo = g.vgeo.astype(np.float64), g.sgeo.astype(np.float64)
     g64.D = [d.astype(np.float64) for d in g.D]
     m64 = oatmos.DryAtmosModel(np.float64, orientation=model.orientation, ref_state=model.ref_state,
-                               turbulence=model.turbulence, sources=model.sources, bcs=model.bcs)
+                               turbulence=model.turbulence, sources=model.sources, bcs=model.bcs,
+                               hyperdiffusion=getattr(model, "hyperdiffusion", None))
     out = {}
     tend = {}
     aux32 = odg.DGModel(model, [g], nf, skip_zero_viscosity=skip_zero_viscosity,
@@ -561,7 +562,7 @@ def balance_case(config="GCM", nf="roe", nsteps=10):
 
 
 def hyperdiffusion_case(kind="sphere", nsteps=2, turbulence=("constant_kinematic", 0.0, False),
-                        tau=None, nf="rusanov"):
+                        tau=None, nf="rusanov", FT=np.float64):
     """DryBiharmonic(tau) with diffusion_direction = HorizontalDirection(), as the GCM
     drivers configure it (experiments/TestCase/baroclinic_wave.jl:179, AtmosGCM/heldsuarez.jl:195).
     kind: "sphere" (cubed sphere, panel flips), "box" (flat box, periodic horizontally), "walled_box"
@@ -572,19 +573,21 @@ def hyperdiffusion_case(kind="sphere", nsteps=2, turbulence=("constant_kinematic
     # relative size there
     hyp = ("dry_biharmonic", tau or (8 * 3600.0 if kind == "sphere" else 30.0))
     if kind == "sphere":
-        model, gs = gcm_setup(3, 2, turbulence=turbulence, hyperdiffusion=hyp)
-        model0, _ = gcm_setup(3, 2, turbulence=turbulence)
+        model, gs = gcm_setup(3, 2, FT=FT, turbulence=turbulence, hyperdiffusion=hyp)
+        model0, _ = gcm_setup(3, 2, FT=FT, turbulence=turbulence)
         dt = 0.5
     else:
         pxy = (True, True) if kind == "box" else (False, False)
-        model, gs = box_setup((3, 2, 3), turbulence=turbulence, hyperdiffusion=hyp, periodic_xy=pxy)
-        model0, _ = box_setup((3, 2, 3), turbulence=turbulence, periodic_xy=pxy)
+        model, gs = box_setup((3, 2, 3), FT=FT, turbulence=turbulence, hyperdiffusion=hyp, periodic_xy=pxy)
+        model0, _ = box_setup((3, 2, 3), FT=FT, turbulence=turbulence, periodic_xy=pxy)
         dt = 0.01
     g = gs[0]
     odgm = odg.DGModel(model, [g], nf, diffusion_direction="horizontal")
     aux = np.moveaxis(odgm.state_auxiliary[0].data[:g.nreal], 1, 0)
     Q0 = oatmos.init_baroclinic_wave(model, aux) if kind == "sphere" else bubble_state(model, g, aux)
     res = compare_case(model, g, Q0, nf=nf, nsteps=nsteps, dt=dt, diffusion_direction="horizontal")
+    if FT == np.float32:
+        return res
     # the hyperdiffusion's own contribution: tendency(with) - tendency(without), oracle and device
     P = pkg()
     tend = {}
@@ -694,3 +697,108 @@ def ocean_refvals_on_device():
             out[(name, ivar)] = oocean.statecheck(w, ivar)
     dg.close()
     return out
+
+
+def ocean_windstress_on_device():
+    """test/Ocean/HydrostaticBoussinesq/test_windstress_short.jl (explicit) run entirely through libcmdg:
+    HomogeneousBox with (NoSlip, Insulating) sides, (FreeSlip, Insulating) bottom, (KinematicStress,
+    Insulating) surface -- the ocean boundary-condition branches the gyre does not use -- 20 LSRK144
+    steps of 180 s; returns min/max/mean/std per field and the oracle's final state difference."""
+    from oracle import ocean as oocean
+    from tests.test_oracle_ocean_windstress import HomogeneousBox
+    P = pkg()
+    Lx, Ly, H = 1e6, 1e6, 400.0
+    br = (np.linspace(0, Lx, 6), np.linspace(0, Ly, 6), np.linspace(-H, 0, 6))
+    topo = tp.StackedBrickTopology(1, br, periodicity=(False, False, False), boundary=((1, 1), (1, 1), (2, 3)))
+    g = ogrids.Grid(topo[0], 4)
+    prob = HomogeneousBox(Lx, Ly, H)
+    xi = g.xi[2]
+    bcs = (("noslip", "insulating"), ("freeslip", "insulating"), ("kinematic_stress", "insulating"))
+    model = oocean.HBModel(prob, bcs=bcs, vert_filter=oocean.cutoff_filter_matrix(xi, 3),
+                           exp_filter=oocean.exponential_filter_matrix(xi, 1, 8))
+    odgm = odg.DGModel(model, [g], "rusanov")
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    dgrid = P.DiscontinuousSpectralElementGrid(
+        g.N[0], g.vgeo, g.sgeo, g.vmapM, g.vmapP, g.elemtobndy, g.D[0], g.nreal,
+        interiorelems=g.interiorelems, exteriorelems=g.exteriorelems,
+        nvertelem=g.topology.stacksize, Imat=g.Imat[2], xi=g.xi[2])
+    pbcs = (P.OceanBC(P.Impenetrable(P.NoSlip()), P.Insulating()),
+            P.OceanBC(P.Impenetrable(P.FreeSlip()), P.Insulating()),
+            P.OceanBC(P.Penetrable(P.KinematicStress()), P.Insulating()))
+    m = P.HBModel(P.HomogeneousBox(Lx, Ly, H, boundary_conditions=pbcs), cʰ=float(model.ch))
+    aux = P.MPIStateArray(dgrid, 8, data=odgm.state_auxiliary[0].data)
+    md = dict(vert_filter=P.CutoffFilter(dgrid, 3), exp_filter=P.ExponentialFilter(dgrid, 1, 8))
+    dg = P.DGModel(m, dgrid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, modeldata=md)
+    dQ = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    # one evaluation first (tendency parity with these boundary conditions), on a spun-up oracle state
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=180.0, t0=0.0)
+    oode.solve(oQ, osol, numberofsteps=2)
+    dQs = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    odQ = [oQ[0].similar()]
+    odgm(odQ, oQ, 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 4)
+    dT.data.fill_(float("nan"))
+    dg(dT, dQs, None, 0.0, 1.0, 0.0)
+    res = {"tendency_rel_l2": rel_l2(dT.realdata.cpu().numpy(), odQ[0].realdata)}
+    sol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=180.0, t0=0.0)
+    P.solve(dQ, sol, numberofsteps=20)
+
+    class Wrap:
+        def __init__(self, t, nreal):
+            self.realdata = t.cpu().numpy()[:nreal]
+    stats = {}
+    for name, arr in (("Q", dQ), ("aux", dg.state_auxiliary)):
+        w = Wrap(arr.data, g.nreal)
+        for ivar in range(4):
+            stats[(name, ivar)] = oocean.statecheck(w, ivar)
+    res["stats"] = stats
+    dg.close()
+    return res
+
+
+def ocean_case_float32(nsteps=2, dt=120.0, nelem=(5, 5, 5), spinup=3):
+    """Float32 instantiation of the four HBModel kernels: the device runs in Float32 on Float32-rounded
+    grid arrays and state; the oracle (Float64 only for the ocean) evaluates the same rounded inputs in
+    Float64 -- i.e. it is the 'truth' of a Float32 run, so the differences are the Float32 rounding of
+    the kernels themselves."""
+    import copy
+    P = pkg()
+    model, gs, prob = ocean_setup(1, nelem)
+    g64 = gs[0]
+    # Float32-rounded geometry, seen by the oracle as Float64 values
+    g = copy.copy(g64)
+    g.vgeo = g64.vgeo.astype(np.float32).astype(np.float64)
+    g.sgeo = g64.sgeo.astype(np.float32).astype(np.float64)
+    odgm = odg.DGModel(model, [g], "rusanov")
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=dt, t0=0.0)
+    oode.solve(oQ, osol, numberofsteps=spinup)
+    oQ[0].data[...] = oQ[0].data.astype(np.float32).astype(np.float64)
+    odgm.state_auxiliary[0].data[...] = odgm.state_auxiliary[0].data.astype(np.float32).astype(np.float64)
+    g32 = copy.copy(g)
+    g32.vgeo, g32.sgeo = g.vgeo.astype(np.float32), g.sgeo.astype(np.float32)
+    dg, dgrid = device_ocean_dg(model, g32, odgm)
+    import torch
+    assert dgrid.FT == torch.float32
+    dQ = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    odQ = [oQ[0].similar()]
+    odgm(odQ, oQ, 0.0, 1, 0)
+    dT = P.MPIStateArray(dgrid, 4)
+    dT.data.fill_(float("nan"))
+    dg(dT, dQ, None, 0.0, 1.0, 0.0)
+    got = dT.realdata.cpu().numpy().astype(np.float64)
+    res = {"tendency_rel_l2": rel_l2(got, odQ[0].realdata),
+           "tendency_per_state_rel_l2": [rel_l2(got[:, s], odQ[0].realdata[:, s]) for s in range(4)],
+           "gradflux_rel_l2": rel_l2(dg.state_gradient_flux.realdata.cpu().numpy(), odgm.state_gradient_flux[0].realdata),
+           "aux_rel_l2": rel_l2(dg.state_auxiliary.realdata[:, 1:4].cpu().numpy(), odgm.state_auxiliary[0].realdata[:, 1:4])}
+    osol2 = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=dt, t0=0.0)
+    oode.solve(oQ, osol2, numberofsteps=nsteps)
+    dsol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=dt, t0=0.0)
+    P.solve(dQ, dsol, numberofsteps=nsteps)
+    gotQ = dQ.realdata.cpu().numpy().astype(np.float64)
+    res["state_rel_l2"] = rel_l2(gotQ, oQ[0].realdata)
+    res["state_per_field_rel_l2"] = [rel_l2(gotQ[:, s], oQ[0].realdata[:, s]) for s in range(4)]
+    res["finite"] = bool(np.isfinite(gotQ).all())
+    dg.close()
+    return res
