@@ -77,6 +77,7 @@ struct cmdg_handle_s {
   int device = 0; // CUDA device current at cmdg_create (the handle's GPU)
   size_t fb = 8;  // bytes per float
   bool aux_model = false, visc = false;
+  int tail_pf = 1036;     // tail prefetch for the next launch: one wave (148 SMs x 5 blocks) + pf_dist elements (CMDG_TAILPF)
   int pf_dist = 296;      // L2 prefetch distance of the one-shot tendency kernel: 2 blocks per SM ahead (CMDG_PF overrides)
   // caller-owned device arrays
   void *aux = nullptr, *gradflux = nullptr;
@@ -125,7 +126,7 @@ struct cmdg_handle_s {
   // Measured at 2 GPUs, LSRK54 steps/s: 331 (serial, normal-priority NCCL stream) -> 339 (high-priority
   // NCCL stream) -> 344 (+ this chain).
   cudaStream_t ext_stream = nullptr;
-  cudaEvent_t ev_ext = nullptr, ev_int = nullptr;
+  cudaEvent_t ev_ext = nullptr, ev_int = nullptr, ev_extk = nullptr;
   bool overlap_exterior = true;
   bool exchange_open = false;
   // bookkeeping
@@ -612,9 +613,20 @@ int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double
   };
   auto column = [&](int64_t elem0, int64_t nelems, int set_wz0) -> int {
     if (nelems <= 0) return 0;
-    hb_column_kernel<R, 5><<<(unsigned)(nelems / nv), 32, 0, st>>>(
-        (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
-        P.alphaT, nv, (int)elem0, set_wz0);
+    // segmented scan (one block per stack, 32 element slots x 25 horizontal nodes) unless the stack is too
+    // tall for the shared-memory carries or CMDG_HB_SERIAL_COLUMN asks for the reference-like serial march
+    constexpr int SLOTS = 32;
+    const size_t carry_bytes = (size_t)2 * nv * 25 * sizeof(R);
+    static const bool serial = getenv("CMDG_HB_SERIAL_COLUMN") != nullptr;
+    if (!serial && carry_bytes <= 40 * 1024) {
+      hb_column_scan_kernel<R, 5, SLOTS><<<(unsigned)(nelems / nv), SLOTS * 25, carry_bytes, st>>>(
+          (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
+          P.alphaT, nv, (int)elem0, set_wz0);
+    } else {
+      hb_column_kernel<R, 5><<<(unsigned)(nelems / nv), 32, 0, st>>>(
+          (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
+          P.alphaT, nv, (int)elem0, set_wz0);
+    }
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -853,6 +865,7 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   const bool overlap = par && !h->is_hb && !h->visc && !h->ntracers && h->step_filter_target < 0 && h->overlap_exterior &&
                        h->ext_stream && h->nexterior > 0 && h->ninterior > 0;
   cudaStream_t xs = h->ext_stream;
+  bool ext_pending = false;
   if (overlap) {
     if (int rc = ensure_const_D<R>(h, st)) return rc;
     CU(cudaEventRecord(h->ev_int, st));
@@ -905,23 +918,38 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       const bool gf_needed = h->hyper && (h->d.turbulence == CMDG_TURB_SMAGORINSKY || h->d.turb_param != 0.0);
       if (s != nstage - 1 && !gf_needed) ga.gradflux = nullptr;
       int rc;
+      // tail prefetch (Euler path): the last blocks of this stage's (last) launch warm L2 for the first
+      // wave(s) of the next stage's launch(es): CMDG_TAILPF = number of elements per next launch (0 = off)
+      const int tailpf = (h->visc || s == nstage - 1 && step + 1 == nsteps) ? 0 : h->tail_pf;
+      a.pfn_Q = nxt;
       if (!par) {
         if (h->visc && (rc = second_order_passes<R>(h, ga, cur, false, true, false, st))) return rc;
         a.elems = nullptr;
+        a.pfn_list[0] = nullptr;
+        a.pfn_n[0] = (int)std::min<int64_t>(nreal, tailpf);
         if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
       } else {
         if (overlap) {
           a.elems = h->exterior;
           if ((rc = launch_tendency<R>(h, a, h->nexterior, xs))) return rc;
+          // interior elements never read ghosts: the next stage's interior kernel only needs this exterior
+          // KERNEL (the real exterior elements of the new state), not the halo that follows it
+          CU(cudaEventRecord(h->ev_extk, xs));
           if ((rc = exchange_begin_t<R>(h, nxt, h->d.nstate, xs))) return rc;
           if ((rc = exchange_end_t<R>(h, nxt, h->d.nstate, xs))) return rc;
           CU(cudaEventRecord(h->ev_ext, xs));
           a.elems = h->interior;
+          a.pfn_list[0] = h->exterior;
+          a.pfn_n[0] = (int)std::min<int64_t>(h->nexterior, tailpf);
+          a.pfn_list[1] = h->interior;
+          a.pfn_n[1] = (int)std::min<int64_t>(h->ninterior, tailpf);
           if ((rc = launch_tendency<R>(h, a, h->ninterior, st))) return rc;
           CU(cudaEventRecord(h->ev_int, st));
-          // the next stage's kernels read what both streams wrote
+          // next stage: the exterior kernel (side stream, after its own unpack) needs this interior kernel;
+          // the interior kernel (main stream, back to back with this one) needs this exterior kernel
           CU(cudaStreamWaitEvent(xs, h->ev_int, 0));
-          CU(cudaStreamWaitEvent(st, h->ev_ext, 0));
+          CU(cudaStreamWaitEvent(st, h->ev_extk, 0));
+          ext_pending = true;
           R *tmp = cur;
           cur = nxt;
           nxt = tmp;
@@ -953,6 +981,8 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
     }
   }
   h->tl_on = false;
+  // the caller's stream sees the last halo (ghosts of the final state) as well
+  if (ext_pending) CU(cudaStreamWaitEvent(st, h->ev_ext, 0));
   if (cur != (R *)Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
   // the reference leaves dQ scaled by RKA[1] after the last stage (:130-141)
   const size_t n = (size_t)nreal * h->d.nstate * h->Np;
@@ -1228,6 +1258,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   h->hyper = hyp;
   h->ntracers = nt;
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
+  if (const char *kv = getenv("CMDG_TAILPF")) h->tail_pf = atoi(kv);
   if (const char *kv = getenv("CMDG_TIMELINE")) h->tl_path = kv;
   if (const char *kv = getenv("CMDG_OVERLAP")) h->overlap_exterior = atoi(kv) != 0;
   // the NCCL send/recv kernel is launched while the interior kernel still has thousands of blocks
@@ -1243,6 +1274,7 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (e1 == cudaSuccess) e1 = cudaStreamCreateWithPriority(&h->ext_stream, cudaStreamNonBlocking, prio_hi);
   if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming);
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming);
+  if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_extk, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     delete h;
     return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
@@ -1268,6 +1300,7 @@ int cmdg_destroy(cmdg_handle h) {
   if (h->ext_stream) cudaStreamDestroy(h->ext_stream);
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   if (h->ev_int) cudaEventDestroy(h->ev_int);
+  if (h->ev_extk) cudaEventDestroy(h->ev_extk);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   delete h;

@@ -68,7 +68,7 @@ struct TendArgs {
   R *dQ;               // [nelem][5][Np]
   R *Qout;             // fused RK update target (may alias nothing in Q); NULL = no update
   R *aux_out;          // write theta_v / air_T here (NULL = don't)
-  const R *vgeoP;      // [nreal][Np][10]  M*xi{m}x{d} (m-major), MI  (80 B per node)
+  const R *vgeoP;      // [nreal][5][Np] pairs: M*xi{m}x{d} (m-major) c = 0..8, MI c = 9; pair p = (c 2p, c 2p+1)  (80 B per node)
   const R *sgeoP;      // [nreal][6*Nfp][4]  n1,n2,n3, sM*vMI         (32 B per face node)
   const int2 *conn;    // [nreal][6]  x = neighbour element (0-based), y = meta
   const int *elems;    // launch list (0-based element ids) or NULL for identity
@@ -81,6 +81,13 @@ struct TendArgs {
   const R *F2;         // [nelem][12][Np]   F2[d][s], s = 1..4, at column 4*d + s-1 (ghosts by exchange)
   const R *Fn;         // [nreal][6*Nfp][4] n . F2 at the element's own face nodes
   int nreal;
+  // tail prefetch: the last pfn_n[0] + pfn_n[1] blocks of this launch pull the inputs of the first
+  // elements of the NEXT launch(es) into L2 (their first wave would otherwise start on cold DRAM misses:
+  // the stage's output was written ~0.5 ms -- several L2 capacities -- earlier).  pfn_list[i] = launch
+  // list of the next launch (NULL = identity), pfn_Q = the state it will read (this launch's Qout).
+  const int *pfn_list[2];
+  int pfn_n[2];
+  const R *pfn_Q;
 };
 
 // conn.y layout: bits 0-2 neighbour face (0..5), bit 3 flip of first face index,
@@ -105,18 +112,23 @@ template <class R> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
 template <> struct Vec2<float> { typedef float2 type; };
 
-// node geometry (10 words) / face-node geometry (4 words) as vector loads
+// node geometry (10 words) / face-node geometry (4 words) as vector loads.
+// vgeoP is stored as five pair columns per element, [e][5][Np] of (2 words): lane n of a warp reads pair
+// c at ((e * 5 + c) * Np + n), i.e. one warp-level load covers 32 x 16 contiguous bytes = 4-5 cache lines.
+// (Round 1 stored [e][Np][10]: the same five 16-byte loads per thread then had an 80-byte lane stride and
+// touched 20 lines each -- 400 L1 tag requests per element, 39 % of all global requests of the tendency
+// kernel, whose limiter is the L1 / LSU pipe.)
 template <class R>
-__device__ __forceinline__ void load_vgeo(const R *__restrict__ p, R g[9], R &MI) {
+__device__ __forceinline__ void load_vgeo(const R *__restrict__ vgeoP, int e, int n, int Np, R g[9], R &MI) {
   typedef typename Vec2<R>::type V;
-  const V *__restrict__ v = reinterpret_cast<const V *>(p);
+  const V *__restrict__ v = reinterpret_cast<const V *>(vgeoP) + (size_t)e * 5 * Np + n;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const V x = v[c];
+    const V x = v[(size_t)c * Np];
     g[2 * c] = x.x;
     g[2 * c + 1] = x.y;
   }
-  const V x = v[4];
+  const V x = v[(size_t)4 * Np];
   g[8] = x.x;
   MI = x.y;
 }
@@ -134,6 +146,9 @@ __device__ __forceinline__ void load_sgeo(const R *__restrict__ p, R n[3], R &sM
 template <class R> __device__ __forceinline__ R rsqrt_(R x);
 template <> __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 template <> __device__ __forceinline__ float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+template <class R> __device__ __forceinline__ R fast_rsqrt_(R x);
+template <> __device__ __forceinline__ double fast_rsqrt_(double x) { return rsqrt(x); }
+template <> __device__ __forceinline__ float fast_rsqrt_(float x) { return rsqrtf(x); }
 template <class R> __device__ __forceinline__ R sqrt_(R x);
 template <> __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
@@ -423,7 +438,20 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr int BLOCK = Dims<NQ>::BLOCK;
   constexpr int NWARP = BLOCK / 32;
   constexpr int FSTRIDE = (NWARP - 1) * 32;              // face threads per block
-  constexpr int NITEM = (NFN + FSTRIDE - 1) / FSTRIDE;   // face items per face thread
+  // Face-aligned items: when a face fits a warp and the faces divide evenly among the face warps, face
+  // warp w owns faces w, w + (NWARP-1), ... and lane = face node.  Same number of rounds as packing the
+  // 6 Nfp items densely (2 for Nq = 5), but a warp never straddles two faces, which is what made the
+  // minus-side reads S.Q[s][vm] (stride 5 / 25 doubles) collide in shared-memory banks: with one face
+  // per warp every half-warp access of the face phase is conflict-free except the xi2-faces' first one.
+  // Measured (ncu, 61 440 elements, profiles/r2_ncu_full_dg_tendency_baroclinic_face_aligned.txt): excessive
+  // shared wavefronts 8.5 M -> 3.8 M (14 % -> 6 % of all), but the second round then runs three 25-lane
+  // warps instead of 54 dense lanes: +12 % warp instructions, 945 k -> 963 k cycles.  Net loss, so the
+  // dense packing stays the default (-DCMDG_FACE_ALIGNED=1 selects this mapping).
+#ifndef CMDG_FACE_ALIGNED
+#define CMDG_FACE_ALIGNED 0
+#endif
+  constexpr bool FALIGN = CMDG_FACE_ALIGNED && (NFP <= 32) && (6 % (NWARP - 1) == 0);
+  constexpr int NITEM = FALIGN ? 6 / (NWARP - 1) : (NFN + FSTRIDE - 1) / FSTRIDE;   // face items per face thread
   static_assert(NWARP >= 2 && NQ * 5 <= 32, "plane contraction: one warp holds Nq x 5 (plane, state) pairs");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TendSmem<R, NQ, AUX, VISC> &S = *reinterpret_cast<TendSmem<R, NQ, AUX, VISC> *>(smem_raw);
@@ -442,11 +470,14 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   // gathers (cp.async) the neighbour traces of exactly the items it will later compute.
   const int warp = tid >> 5, lane = tid & 31;
   const int cw = blockIdx.x % NWARP;
-  const int ft = (warp == cw) ? -1 : ((warp < cw ? warp : warp - 1) * 32 + lane);
+  const int fw = warp < cw ? warp : warp - 1;             // face-warp index (unused by the contraction warp)
+  const int ft = (warp == cw) ? -1 : (FALIGN ? (lane < NFP ? 0 : -1) : fw * 32 + lane);
+  // item of round r: dense (ft + r * FSTRIDE) or face-aligned ((fw + r (NWARP-1)) Nfp + lane)
+#define CMDG_ITEM(r) (FALIGN ? ((ft >= 0) ? (fw + (r) * (NWARP - 1)) * NFP + lane : NFN) : ft + (r) * FSTRIDE)
   int2 cn[NITEM];
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = ft + r * FSTRIDE;
+    const int it = CMDG_ITEM(r);
     cn[r] = (ft >= 0 && it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
     // face geometry of my items is needed only in the face phase: park it in L1 now
     if (ft >= 0 && it < NFN)
@@ -476,6 +507,25 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       if (en < A.nreal) prefetch_l2_bulk(A.Fn + (size_t)en * NFN * 4, (size_t)NFN * 4 * sizeof(R));
     }
     asm volatile("prefetch.global.L2 [%0];" ::"l"(A.conn + (size_t)en * 6));
+  }
+  // ---- tail prefetch for the next launch(es), by the last blocks of this one ----
+  if (tid == BLOCK - 2 && A.pfn_n[0] + A.pfn_n[1] > 0) {
+    const int back = (int)gridDim.x - 1 - (int)blockIdx.x;     // 0 for the last block
+    if (back < A.pfn_n[0] + A.pfn_n[1]) {
+      const int li = back < A.pfn_n[0] ? 0 : 1;
+      const int j = li == 0 ? back : back - A.pfn_n[0];
+      const int en = A.pfn_list[li] ? A.pfn_list[li][j] : j;
+      prefetch_l2_bulk(A.pfn_Q + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
+      prefetch_l2_bulk(A.dQ + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
+      prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
+      prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R));
+      if (AUX) {
+        const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
+        const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
+        if (lo >= 0 && hi > lo)
+          prefetch_l2_bulk(auxg + ((size_t)en * P.naux + lo) * NP, (size_t)(hi - lo) * NP * sizeof(R));
+      }
+    }
   }
 
   // ---- (b) issue my node's loads ----
@@ -510,13 +560,13 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
       for (int c = 0; c < 12; ++c) f2[c] = A.F2[eoffF + (size_t)c * NP];
     }
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
   }
 
   // ---- (c) asynchronous gathers of the neighbour traces into shared memory ----
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = ft + r * FSTRIDE;
+    const int it = CMDG_ITEM(r);
     if (ft >= 0 && it < NFN && ((cn[r].y >> 4) & 15) == 0) {
       const int fn = it % NFP;
       int a = fn % NQ;
@@ -556,7 +606,8 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     }
     if (A.aux_out) {
       // kernel_nodal_update_auxiliary_state! / DryModel (moisture.jl:58-69)
-      A.aux_out[eoffA + (size_t)P.a_theta_v * NP + tid] = th.T / pow_<R>(th.p / P.MSLP, P.kappa);
+      // (p / MSLP)^kappa as exp(kappa log(.)) as in the gradient kernel: half the instructions of pow
+      A.aux_out[eoffA + (size_t)P.a_theta_v * NP + tid] = th.T / exp_<R>(P.kappa * log_<R>(th.p / P.MSLP));
       A.aux_out[eoffA + (size_t)P.a_T * NP + tid] = th.T;
     }
     const R u[3] = {q[1] * th.rinv, q[2] * th.rinv, q[3] * th.rinv};
@@ -678,7 +729,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
-    const int it = ft + r * FSTRIDE;
+    const int it = CMDG_ITEM(r);
     if (it >= NFN) break;
     const int f = it / NFP, fn = it - f * NFP;
     const int2 c = cn[r];
@@ -736,8 +787,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) fl[s] = R(0.5) * (fm[s] + fp[s]);
     if (NF1 == NF_RUSANOV) {
-      const R cm = sqrt_<R>(P.gamma * tm.p * tm.rinv);
-      const R cp = sqrt_<R>(P.gamma * P.R_d * tp.T);
+      // sound speeds as x * rsqrt(x) (x > 0): ~40 % fewer instructions than the correctly rounded sqrt, which
+      // was the single largest instruction consumer of the kernel (4.9 %); 1-2 ulp in a wave-speed bound
+      const R c2m = P.gamma * tm.p * tm.rinv, c2p = P.gamma * P.R_d * tp.T;
+      const R cm = c2m * fast_rsqrt_<R>(c2m);
+      const R cp = c2p * fast_rsqrt_<R>(c2p);
       const R lam = R(0.5) * fmax(fabs(unm) + cm, fabs(unp) + cp);
 #pragma unroll
       for (int s = 0; s < 5; ++s) fl[s] += lam * (qm[s] - qp[s]);
@@ -805,6 +859,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
     }
   }
+#undef CMDG_ITEM
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1196,7 +1251,7 @@ dg_gradient_kernel(const GradArgs<R> A, const AtmosParams<R> P) {
       for (int d = 0; d < 3; ++d) gPhi[d] = A.aux[eoffA + (size_t)(P.a_gradPhi + d) * NP + tid];
     }
     if (!HYPER && AUX && P.a_Delta >= 0 && A.F2) Delta = A.aux[eoffA + (size_t)P.a_Delta * NP + tid];
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
     gradient_argument<R>(P, q, Phi, G);
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
@@ -1471,7 +1526,7 @@ hyper_divergence_kernel(const HyperArgs<R> A) {
     const size_t eo = (size_t)e * 12 * NP + tid;
 #pragma unroll
     for (int c = 0; c < 12; ++c) gr[c] = A.Qhg[eo + (size_t)c * NP];
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
 #pragma unroll
     for (int c = 0; c < 12; ++c) sGr[c][tid] = gr[c];
 #pragma unroll
@@ -1585,7 +1640,7 @@ hyper_flux_kernel(const HyperArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) q[s] = A.Q[(size_t)e * P.nstate * NP + (size_t)s * NP + tid];
     const R hD = A.aux[eoffA + (size_t)P.a_Delta_h * NP + tid] * R(0.5);
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
     if (viscous) {
       // issued early: consumed after the face terms
       const size_t eoffG = (size_t)e * P.ngradflux * NP + tid;
@@ -1719,7 +1774,7 @@ __global__ void unpack_kernel(R *__restrict__ buf, const R *__restrict__ recvbuf
 }
 
 // Packed private geometry (built once in cmdg_bind_grid).
-//   vgeoP[e][n][c], c = 3*m + d : M * d(xi_{m+1})/d(x_{d+1});  c = 9 : MI
+//   vgeoP[e][c / 2][n][c % 2], c = 3*m + d : M * d(xi_{m+1})/d(x_{d+1});  c = 9 : MI
 //   (reference vgeo columns, Grids.jl:76-92: xi{m}x{d} at 3*(d-1)+(m-1), M = 9, MI = 10)
 template <class R>
 __global__ void pack_vgeo_kernel(R *__restrict__ out, const R *__restrict__ vgeo, int Np,
@@ -1729,11 +1784,15 @@ __global__ void pack_vgeo_kernel(R *__restrict__ out, const R *__restrict__ vgeo
   const size_t e = idx / Np;
   const int n = (int)(idx - e * Np);
   const R *v = vgeo + e * (size_t)nvgeo * Np + n;
-  R *o = out + (e * (size_t)Np + n) * 10;
+  // pair-column layout: word c of node n at ((e * 5 + c / 2) * Np + n) * 2 + c % 2
+  R *o = out + e * (size_t)Np * 10;
   const R M = v[(size_t)9 * Np];
   for (int m = 0; m < 3; ++m)
-    for (int d = 0; d < 3; ++d) o[3 * m + d] = M * v[(size_t)(3 * d + m) * Np];
-  o[9] = v[(size_t)10 * Np];
+    for (int d = 0; d < 3; ++d) {
+      const int c = 3 * m + d;
+      o[((size_t)(c / 2) * Np + n) * 2 + c % 2] = M * v[(size_t)(3 * d + m) * Np];
+    }
+  o[((size_t)4 * Np + n) * 2 + 1] = v[(size_t)10 * Np];
 }
 //   sgeoP[e][f*Nfp + n][c], c = 0..2 unit normal, c = 3 : sM * vMI
 //   (reference sgeo[c, n, f, e], Grids.jl:129-146)

@@ -180,7 +180,7 @@ hb_gradient_kernel(const HBArgs<R> A, const HBParams<R> P) {
   const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   if (tid < NP) {
     R g[9], MI;
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
 #pragma unroll
     for (int c = 0; c < 9; ++c) g[c] *= MI;
     R G1[3] = {0, 0, 0}, G2[3] = {0, 0, 0}, G3[3] = {0, 0, 0};
@@ -279,6 +279,88 @@ __global__ void hb_column_kernel(R *__restrict__ aux, const R *__restrict__ Q,
   }
 }
 
+// The same as a segmented scan: one block per stack, thread = (element slot, horizontal node).  Every
+// element's local integral (carry 0) is independent; only the element-top values chain up the stack
+// (kernel_indefinite_stack_integral!, DGModel_kernels.jl:1903-2007, carries them in a serial k-loop, one
+// thread per (i, j) and a whole stack per thread: 2.7 warps per SM at 20 x 20 stacks and 50 dependent
+// DRAM round trips -- 114 us, 21 % of an ocean stage).  Pass 1: tops of all elements in parallel -> shared
+// memory; exclusive prefix over the stack by the first slot's threads; pass 2: local integrals again (the
+// inputs are L1/L2 hits) + carry, reverse integral (:2009-2104) and wz0.  Dynamic shared memory:
+// 2 * nvert * Nq^2 values.  Differs from the serial kernel in rounding order only.
+template <class R, int NQ, int SLOTS>
+__global__ void __launch_bounds__(SLOTS * NQ * NQ)
+hb_column_scan_kernel(R *__restrict__ aux, const R *__restrict__ Q, const R *__restrict__ gradflux,
+                      const R *__restrict__ JcV, const R *__restrict__ Imat, R alphaT, int nvert, int elem0,
+                      int set_wz0) {
+  constexpr int NP = Dims<NQ>::NP, NQH = NQ * NQ;
+  extern __shared__ __align__(16) unsigned char hb_col_smem[];
+  R *topw = reinterpret_cast<R *>(hb_col_smem);     // [nvert][NQH]
+  R *topp = topw + (size_t)nvert * NQH;             // [nvert][NQH]
+  __shared__ R sI[NQ * NQ];
+  __shared__ R tot[2][NQH];
+  const int tid = threadIdx.x;
+  const int ij = tid % NQH, slot = tid / NQH;
+  if (tid < NQ * NQ) sI[tid] = Imat[tid];
+  const int e0 = elem0 + blockIdx.x * nvert;
+  __syncthreads();
+  // pass 1: element tops (row Nq-1 of Imat applied to the integrands)
+  for (int ev = slot; ev < nvert; ev += SLOTS) {
+    const size_t e = (size_t)(e0 + ev);
+    R tw = 0, tp = 0;
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const int nn = ij + NQH * n;
+      const R jc = JcV[e * NP + nn];
+      tw += sI[(NQ - 1) * NQ + n] * (-gradflux[(e * HB_GF + 0) * NP + nn] * jc);
+      tp += sI[(NQ - 1) * NQ + n] * ((-alphaT * Q[(e * HB_S + 3) * NP + nn]) * jc);
+    }
+    topw[ev * NQH + ij] = tw;
+    topp[ev * NQH + ij] = tp;
+  }
+  __syncthreads();
+  // exclusive prefix up the stack (carry of element ev = integral up to its bottom)
+  if (slot == 0) {
+    R cw = 0, cp = 0;
+    for (int ev = 0; ev < nvert; ++ev) {
+      const R tw = topw[ev * NQH + ij], tp = topp[ev * NQH + ij];
+      topw[ev * NQH + ij] = cw;
+      topp[ev * NQH + ij] = cp;
+      cw += tw;
+      cp += tp;
+    }
+    tot[0][ij] = cw;
+    tot[1][ij] = cp;
+  }
+  __syncthreads();
+  const R totw = tot[0][ij], totp = tot[1][ij];
+  // pass 2: w = carry + local integral; pkin = pkin(top of stack) - (carry + local); wz0 = w(top of stack)
+  for (int ev = slot; ev < nvert; ev += SLOTS) {
+    const size_t e = (size_t)(e0 + ev);
+    R kw[NQ], kp[NQ];
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) {
+      const int nn = ij + NQH * n;
+      const R jc = JcV[e * NP + nn];
+      kw[n] = -gradflux[(e * HB_GF + 0) * NP + nn] * jc;
+      kp[n] = (-alphaT * Q[(e * HB_S + 3) * NP + nn]) * jc;
+    }
+    const R cw = topw[ev * NQH + ij], cp = topp[ev * NQH + ij];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      R lw = cw, lp = cp;
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) {
+        lw += sI[k * NQ + n] * kw[n];
+        lp += sI[k * NQ + n] * kp[n];
+      }
+      const int nn = ij + NQH * k;
+      aux[(e * HB_A + 1) * NP + nn] = lw;
+      aux[(e * HB_A + 2) * NP + nn] = totp - lp;
+      if (set_wz0) aux[(e * HB_A + 3) * NP + nn] = totw;
+    }
+  }
+}
+
 template <class R>
 __global__ void extract_column_kernel(R *__restrict__ out, const R *__restrict__ vgeo, int Np,
                                       int nvgeo, int col, size_t nelem) {
@@ -333,7 +415,7 @@ hb_tendency_kernel(const HBArgs<R> A, const HBParams<R> P) {
 #pragma unroll
     for (int s = 1; s < 10; ++s) gf[s] = A.gradflux[eoffG + (size_t)s * NP + tid];
     R g[9];
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
 #pragma unroll
     for (int s = 0; s < HB_S; ++s) sQ[s][tid] = q[s];
     sA[0][tid] = y;

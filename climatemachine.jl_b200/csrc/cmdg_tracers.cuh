@@ -93,7 +93,7 @@ tracer_gradient_kernel(const TracerArgs<R> A, const AtmosParams<R> P) {
   const int i_ = tid % NQ, j_ = (tid / NQ) % NQ, k_ = tid / (NQ * NQ);
   if (tid < NP) {
     R g[9], MI;
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
 #pragma unroll
     for (int c = 0; c < 9; ++c) g[c] *= MI;   // packed copy holds M * xi_x
     R G1[NT], G2[NT], G3[NT];
@@ -192,7 +192,7 @@ tracer_tendency_kernel(const TracerArgs<R> A, const AtmosParams<R> P) {
       if (i < A.nt) x[i] = A.Q[eoffQ + (size_t)(5 + i) * NP + tid];
       sX[i][tid] = x[i];
     }
-    load_vgeo<R>(A.vgeoP + ((size_t)e * NP + tid) * 10, g, MI);
+    load_vgeo<R>(A.vgeoP, e, tid, NP, g, MI);
     const R rinv = R(1) / q[0];
     const R u[3] = {q[1] * rinv, q[2] * rinv, q[3] * rinv};
 #pragma unroll
