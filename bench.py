@@ -60,6 +60,14 @@ def algorithmic_bytes_per_node(workload):
         b_eval = w * (3 * S + 11 + A_vol) + 1.2 * (w * (5 + S + A_face) + 8) + w * GFu + 1.2 * w * GFu
         b_stage = b_eval + w * S
         return b_eval, (13 * b_stage + (b_stage - w * S)) / 14
+    if workload == "rising_bubble":
+        # dynamics as row (4) without the Held-Suarez coordinates (A_vol = Phi, grad Phi, rho_ref, p_ref, Delta = 7;
+        # A_face = Phi, p_ref, Delta, grad Phi = 6); the tracer columns have their own kernels (TRACER_BYTES_PER_NODE)
+        S, GF = 5, 10
+        b_tend = w * (3 * S + 11 + 7) + 1.2 * (w * (5 + S + 6) + 8) + w * GF + 1.2 * w * GF
+        b_grad = w * (S + 2 + 9 + GF) + 1.2 * (w * (5 + S + 2) + 8)
+        b_stage = b_tend + w * S
+        return b_tend + b_grad, (13 * b_stage + (b_stage - w * S)) / 14
     if workload == "held_suarez":
         # Euler part + gradient pass + gradient-flux reads in the tendency pass.
         # Tendency launch only (the roofline kernel): A_vol = Phi, grad Phi, rho_ref, p_ref, Delta,
@@ -80,6 +88,13 @@ def algorithmic_bytes_per_node(workload):
     return b_eval, (4 * b_stage + b_stage_first) / 5
 
 
+# passive tracers (NTracers{4}), same counting rules.  tracer_tendency_kernel: rho, rho u (4) + rho chi (4) + dQ chi
+# read (4) and written (4) + new state (4) + own diffusive flux (12) + geometry (11), per face node face geometry (5),
+# the neighbour's rho, rho u, rho chi (8), its diffusive flux (12) and one index; tracer_gradient_kernel: rho, rho chi
+# (5) + nu (3) + delta_chi (4) + 9 metrics, writes the diffusive flux (12) (+ grad chi (12) on the last stage), per face
+# node face geometry (5) + the neighbour's rho, rho chi (5) + one index
+TRACER_BYTES_PER_NODE = {"tracer_tendency": 8 * (4 + 4 + 4 + 4 + 4 + 12 + 11) + 1.2 * (8 * (5 + 8 + 12) + 8),
+                         "tracer_gradient": 8 * (5 + 3 + 4 + 9 + 12) + 1.2 * (8 * (5 + 5) + 8)}
 GRADIENT_BYTES_PER_NODE = 8 * (5 + 2 + 9 + 10) + 1.2 * (8 * (5 + 5 + 2) + 8)   # SURVEY 8(d) B_2nd gradient pass
 
 
@@ -180,6 +195,13 @@ def build_grid(P, workload, ne, nvert, rank, nranks, device):
               np.linspace(-prob.H, 0, nvert + 1))
         topo = tp.stacked_brick_topology(br, (False, False, False), ((1, 1), (1, 1), (2, 3)), rank, nranks)
         return gr.build_grid(topo, 4, torch.float64, None, device), prob
+    if workload == "rising_bubble":
+        # BASELINE.json configs[0] (tutorials/Atmos/risingbubble.jl) at benchmark size: 500 m elements, 10 km deep
+        # (20 levels as the tutorial), ne x ne/4 elements horizontally per GPU (the tutorial: 20 x 1), periodic x / y
+        br = (np.linspace(0, 500.0 * ne * nranks, ne * nranks + 1), np.linspace(0, 500.0 * max(ne // 4, 1), max(ne // 4, 1) + 1),
+              np.linspace(0, 10000.0, nvert + 1))
+        topo = tp.stacked_brick_topology(br, (True, True, False), ((0, 0), (0, 0), (1, 2)), rank, nranks)
+        return gr.build_grid(topo, 4, torch.float64, None, device), None
     L = 0.05
     br = tuple(np.linspace(-L, L, ne + 1) for _ in range(3))
     topo = tp.brick_topology(br, (True, True, True), None, rank, nranks)
@@ -208,6 +230,16 @@ def build_case(P, workload, ne, nvert, rank, nranks, device, hyper=False, skip_z
         dg = P.DGModel(model, grid, *nf, state_auxiliary=aux, diffusion_direction=P.HorizontalDirection(),
                        skip_zero_viscosity=not second, write_aux_diagnostics=True)
         return dict(grid=grid, model=model, dg=dg, aux=aux, dt=dt, ai=ai, skip=not second)
+    if workload == "rising_bubble":
+        # as the tutorial ships it: SmagorinskyLilly(0.21), DryAdiabaticProfile(300 K, 0 K), Gravity, NTracers{4}
+        # with delta_chi = (1, 2, 3, 4), Rusanov, LSRK144NiegemannDiehlBusch
+        model = P.AtmosModel(orientation=P.FlatOrientation(),
+                             ref_state=P.HydrostaticState(P.DryAdiabaticProfile(300.0, 0.0)),
+                             turbulence=P.SmagorinskyLilly(0.21), source=(P.Gravity(),),
+                             boundaryconditions=(P.AtmosBC(), P.AtmosBC()), tracers=P.NTracers((1.0, 2.0, 3.0, 4.0)))
+        aux = P.MPIStateArray(grid, model.number_states("Auxiliary"))
+        dg = P.DGModel(model, grid, *nf, state_auxiliary=aux, write_aux_diagnostics=True)
+        return dict(grid=grid, model=model, dg=dg, aux=aux, dt=0.4, ai=ai, skip=False)
     model = P.AtmosModel()
     aux = P.MPIStateArray(grid, model.number_states("Auxiliary"))
     dg = P.DGModel(model, grid, *nf, state_auxiliary=aux, skip_zero_viscosity=skip_zero_viscosity,
@@ -224,7 +256,7 @@ def init_case(P, case, workload, rank, world, dist):
         dist.broadcast_object_list(uid, src=0)
         dg.comm_init(uid[0], rank, world)
     ocean = workload == "ocean_gyre"
-    Q = P.MPIStateArray(grid, 4 if ocean else 5)
+    Q = P.MPIStateArray(grid, 4 if ocean else model.number_states("Prognostic"))
     if ocean:
         Q.data[:grid.nrealelem] = case["Q0"]
         if world > 1:
@@ -239,15 +271,23 @@ def init_case(P, case, workload, rank, world, dist):
             # (Held-Suarez starts from rest + noise in the tutorial; the baroclinic-wave state gives
             # the friction, relaxation and sponge terms something to act on -- synthetic either way)
             Q.data[:grid.nrealelem] = ai.baroclinic_wave(model, grid, case["aux"])
+        elif workload == "rising_bubble":
+            Q.data[:grid.nrealelem] = ai.rising_bubble(model, grid, case["aux"])
         else:
             Q.data[:grid.nrealelem] = ai.isentropic_vortex(model, grid, 0.0)
-        sol = P.LSRK54CarpenterKennedy(dg, Q, dt=case["dt"], t0=0.0)
+        if workload == "rising_bubble":
+            sol = P.LSRK144NiegemannDiehlBusch(dg, Q, dt=case["dt"], t0=0.0)
+        else:
+            sol = P.LSRK54CarpenterKennedy(dg, Q, dt=case["dt"], t0=0.0)
     return Q, sol
 
 
-def time_steps(P, case, Q, sol, steps, warmup, world, dev, dist, clocks=None):
+def time_steps(P, case, Q, sol, steps, warmup, world, dev, dist, clocks=None, kernel_events=True):
     """Device-resident timing of `steps` steps: barrier + synchronize on both sides, CUDA events on the
-    launching stream, per-launch events inside the library for the kernel classes."""
+    launching stream.  kernel_events: the library additionally brackets every launch with CUDA events (per
+    kernel-class durations for the roofline); those records sit between back-to-back kernels and cost a few
+    microseconds per stage, so `value` is taken from a pass without them and the kernel durations from a
+    second pass of the same steps right after it."""
     import numpy as np
     import torch
     dg = case["dg"]
@@ -275,7 +315,7 @@ def time_steps(P, case, Q, sol, steps, warmup, world, dev, dist, clocks=None):
                 break
             sol.dostep(Q, 0.0, nsteps=5)
             torch.cuda.synchronize()
-    dg.set_timing(not os.environ.get("BENCH_NO_KERNEL_TIMING"))
+    dg.set_timing(bool(kernel_events))
     l0 = dg.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -287,8 +327,8 @@ def time_steps(P, case, Q, sol, steps, warmup, world, dev, dist, clocks=None):
     tc1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = dg.kernel_launches() - l0
-    kern_ms, kern_n = dg.last_kernel_ms()
-    classes = dg.kernel_class_ms()
+    kern_ms, kern_n = dg.last_kernel_ms() if kernel_events else (0.0, 0)
+    classes = dg.kernel_class_ms() if kernel_events else {}
     dg.set_timing(False)
     norm1 = P.norm(Q)
     assert np.isfinite(norm1), "state blew up"
@@ -317,10 +357,16 @@ def workload_name(workload, ne, nvert, world, hyper=False):
     if workload == "ocean_gyre":
         return (f"OceanBoxGCM HBModel ocean gyre, {ne * world}x{ne}x{nvert} elements, N=4, Rusanov, LSRK144 "
                 "(a step = 14 stages), dt=55 s")
+    if workload == "rising_bubble":
+        return (f"rising thermal bubble LES (tutorials/Atmos/risingbubble.jl as shipped: SmagorinskyLilly, NTracers{{4}}, "
+                f"DryAdiabaticProfile), {ne * world}x{max(ne // 4, 1)}x{nvert} elements of 500 m, N=4, Rusanov, LSRK144 "
+                "(a step = 14 stages), dt=0.4 s")
     return f"isentropic vortex, periodic box {ne}^3, N=4, Rusanov, LSRK54"
 
 
 def default_mesh(workload, world, args):
+    if workload == "rising_bubble":
+        return (args.ne or 64), (20 if args.nvert == 10 else args.nvert)
     if workload == "ocean_gyre":
         return (args.ne or 20), (50 if args.nvert == 10 else args.nvert)
     if workload in ("baroclinic_wave", "held_suarez"):
@@ -338,13 +384,17 @@ def secondary_run(P, args, workload, rank, world, dev, dist, steps, grid=None, s
         case["aux0"] = aux0
     Q, sol = init_case(P, case, workload, rank, world, dist)
     ocean = workload == "ocean_gyre"
-    nstate, nstage = (4, 14) if ocean else (5, 5)
-    r = time_steps(P, case, Q, sol, steps, 3, world, dev, dist)
+    nstate, nstage = (4, 14) if ocean else ((9, 14) if workload == "rising_bubble" else (5, 5))
+    r = time_steps(P, case, Q, sol, steps, 3, world, dev, dist, kernel_events=False)
+    rk = time_steps(P, case, Q, sol, steps, 0, world, dev, dist, kernel_events=True)
+    r["kern_ms"], r["kern_n"], r["classes"] = rk["kern_ms"], rk["kern_n"], rk["classes"]
     nodes_local = case["grid"].nrealelem * NP
     cls = r["classes"]
-    (ms, kern_ms, g_ms, hd_ms, hf_ms), (_, _, _, _, _) = reduce_max_sum(
+    other = [k for k in cls if k not in ("tendency", "gradient", "hyper_divergence", "hyper_flux")]
+    red, _ = reduce_max_sum(
         [r["ms"], r["kern_ms"], max(cls["gradient"][0], 0.0), max(cls["hyper_divergence"][0], 0.0),
-         max(cls["hyper_flux"][0], 0.0)], world, dev, dist)
+         max(cls["hyper_flux"][0], 0.0)] + [max(cls[k][0], 0.0) for k in other], world, dev, dist)
+    ms, kern_ms, g_ms, hd_ms, hf_ms = red[:5]
     (_,), (nodes,) = reduce_max_sum([float(nodes_local)], world, dev, dist)
     evals = nstage * steps
     b_eval, b_launch = algorithmic_bytes_per_node(workload)
@@ -361,6 +411,11 @@ def secondary_run(P, args, workload, rank, world, dev, dist, steps, grid=None, s
     if hd_ms > 0:
         out["kernel_ms_per_stage"]["hyper_divergence"] = hd_ms / evals
         out["kernel_ms_per_stage"]["hyper_flux"] = hf_ms / evals
+    for k, v in zip(other, red[5:]):
+        if v > 0:
+            out["kernel_ms_per_stage"][k] = v / evals
+            if k in TRACER_BYTES_PER_NODE:
+                out[f"roofline_{k}_frac"] = nodes_local * TRACER_BYTES_PER_NODE[k] / (v / evals * 1e-3) / 1e9 / peak
     host = None
     if args.keep_host_copy:
         host = (case, Q)
@@ -402,7 +457,7 @@ def run_b200(args):
         parity = bench_checks.parity_block(rank, world, dev)
 
     ocean = args.workload == "ocean_gyre"
-    nstate, nstage = (4, 14) if ocean else (5, 5)
+    nstate, nstage = (4, 14) if ocean else ((9, 14) if args.workload == "rising_bubble" else (5, 5))
     ne, nvert = default_mesh(args.workload, world, args)
     args.nvert = nvert
     case = build_case(P, args.workload, ne, nvert, rank, world, dev, hyper=args.hyperdiffusion)
@@ -414,11 +469,13 @@ def run_b200(args):
     # ---- device-resident timing -------------------------------------------------------
     clocks = ClockSampler(local)
     clocks.start()
-    r = time_steps(P, case, Q, sol, args.steps, args.warmup, world, dev, dist, clocks=clocks)
-    clk = clocks.stop(*r["tc"])
+    r = time_steps(P, case, Q, sol, args.steps, args.warmup, world, dev, dist, clocks=clocks, kernel_events=False)
+    rk = time_steps(P, case, Q, sol, args.steps, 0, world, dev, dist, kernel_events=True)
+    clk = clocks.stop(r["tc"][0], rk["tc"][1])
+    r["kern_ms"], r["kern_n"], r["classes"], r["ms_events"] = rk["kern_ms"], rk["kern_n"], rk["classes"], rk["ms"]
     sustained = None
     if args.steps < 100 and not args.headline_only:
-        r100 = time_steps(P, case, Q, sol, 100, 0, world, dev, dist)
+        r100 = time_steps(P, case, Q, sol, 100, 0, world, dev, dist, kernel_events=False)
         sustained = r100
 
     # ---- end to end through host buffers ------------------------------------------------
@@ -490,6 +547,8 @@ def run_b200(args):
         del keep_grid
         torch.cuda.empty_cache()
         secondary["ocean_gyre"], _ = secondary_run(P, args, "ocean_gyre", rank, world, dev, dist, max(2, ssteps // 4))
+        secondary["rising_bubble_tracers"], _ = secondary_run(P, args, "rising_bubble", rank, world, dev, dist,
+                                                              max(2, ssteps // 4))
 
     if rank != 0:
         if world > 1:
@@ -533,7 +592,10 @@ def run_b200(args):
                      "peak_source": peak_src,
                      "kernel": "hb_tendency_kernel<double,5,RUSANOV>" if ocean else "dg_tendency_kernel<double,5,RUSANOV,...>",
                      "algorithmic_bytes_per_node_per_launch": b_launch_node,
-                     "kernel_ms_per_stage": stage_ms, "launches_per_stage": launches_per_stage},
+                     "kernel_ms_per_stage": stage_ms, "launches_per_stage": launches_per_stage,
+                     "timing": ("per-launch CUDA events in a second pass of the same %d steps right after the pass `value` "
+                                "is taken from (the event records between back-to-back kernels cost a few us per stage): "
+                                "%.4f ms/step with them" % (args.steps, r["ms_events"] / args.steps))},
         "e2e": {"value": dof * nstage * e2e_steps / e2e_s / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": int(nodes_local * nstate * 8),
                 "d2h_bytes_per_step": int(nodes_local * nstate * 8),
@@ -707,7 +769,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="baroclinic_wave", choices=["baroclinic_wave", "vortex", "ocean_gyre", "held_suarez"])
+    ap.add_argument("--workload", default="baroclinic_wave",
+                    choices=["baroclinic_wave", "vortex", "ocean_gyre", "held_suarez", "rising_bubble"])
     ap.add_argument("--ne", type=int, default=0, help="horizontal elements per cube edge / box edge")
     ap.add_argument("--nvert", type=int, default=10)
     ap.add_argument("--hyperdiffusion", action="store_true",

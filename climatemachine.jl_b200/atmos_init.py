@@ -253,6 +253,37 @@ def baroclinic_wave(model, grid, aux):
     return torch.stack([ρ, ρ * uc[0], ρ * uc[1], ρ * uc[2], ρ * e_tot], dim=1).to(grid.FT)
 
 
+def rising_bubble(model, grid, aux, xc=5000.0, zc=2000.0, rc=2000.0, θamplitude=2.0, wind=True):
+    """``init_risingbubble!`` (tutorials/Atmos/risingbubble.jl:106-176): warm bubble on a neutrally stratified
+    column at rest; with NTracers the tutorial's tracer layer (smoothed: the benchmark mesh does not resolve a
+    50 m layer).  `wind` adds a smooth wind (w = 0 on the walls) so that advection, the Rusanov penalty and the
+    Smagorinsky closure all have something to act on -- synthetic either way.  Returns (nreal, 5 + N, Np)."""
+    p = model.param_set
+    lay = aux_layout(model)
+    nr = grid.nrealelem
+    a = aux.data[:nr]
+    x, z = a[:, 0], a[:, 2]
+    r = torch.sqrt((x - xc) ** 2 + (z - zc) ** 2)
+    θ_ref = model.ref_state.virtual_temperature_profile.T_surface
+    θ = θ_ref + torch.where(r <= rc, θamplitude * (1.0 - r / rc), torch.zeros_like(r))
+    π_exner = 1.0 - p.grav / (p.cp_d * θ) * z
+    ρ = p.MSLP / (p.R_d * θ) * π_exner ** (p.cv_d / p.R_d)
+    T = θ * π_exner
+    zero = torch.zeros_like(ρ)
+    Lx = float(x.max()) + 1e-30
+    Lz = float(z.max()) + 1e-30
+    u = [zero, zero, zero]
+    if wind:
+        u = [8 + 2 * torch.sin(2 * math.pi * z / Lz), zero,
+             1.5 * torch.sin(2 * math.pi * x / Lx) * torch.sin(math.pi * z / Lz)]
+    e_kin = 0.5 * (u[0] ** 2 + u[1] ** 2 + u[2] ** 2)
+    cols = [ρ, ρ * u[0], ρ * u[1], ρ * u[2], ρ * (e_kin + a[:, lay["Φ"]] + p.cv_d * (T - p.T_0))]
+    if isinstance(model.tracers, bl.NTracers):
+        ρχ = torch.where((z > 0.04 * Lz) & (z <= 0.16 * Lz), 0.05 * (1 + 0.5 * torch.sin(2 * math.pi * x / Lx)), zero)
+        cols += [ρχ / (i + 1) for i in range(len(model.tracers.δ_χ))]
+    return torch.stack(cols, dim=1).to(grid.FT)
+
+
 def ocean_gyre_state(problem, grid):
     """``ocean_init_state!(::HBModel, ::OceanGyre)`` (ocean_gyre.jl:38-66): state at rest,
     theta = (5 + 4 cos(pi y / Ly)) (1 + z / H).  Returns (Q (nreal,4,Np), aux MPIStateArray)."""

@@ -606,7 +606,9 @@ int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double
     if (n <= 0) return 0;
     HBArgs<R> g = a;
     g.elems = elems;
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
     hb_gradient_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(g, P);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -615,6 +617,7 @@ int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double
     if (nelems <= 0) return 0;
     // segmented scan (one block per stack, 32 element slots x 25 horizontal nodes) unless the stack is too
     // tall for the shared-memory carries or CMDG_HB_SERIAL_COLUMN asks for the reference-like serial march
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), st);
     constexpr int SLOTS = 32;
     const size_t carry_bytes = (size_t)2 * nv * 25 * sizeof(R);
     static const bool serial = getenv("CMDG_HB_SERIAL_COLUMN") != nullptr;
@@ -627,14 +630,17 @@ int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double
           (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
           P.alphaT, nv, (int)elem0, set_wz0);
     }
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), st);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
   };
   // update_auxiliary_state!: vertical filters on the real elements, in place
   if (nreal > 0) {
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), st);
     hb_filter_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>((R *)Q, (const R *)h->Fc,
                                                                        (const R *)h->Fe, (int)nreal);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), st);
     CU(cudaGetLastError());
     h->launches++;
   }
@@ -760,7 +766,9 @@ int eval_with_tracers(cmdg_handle h, void *dQ, const void *Q, void *Qout, double
                    (R *)h->Qhg, h->pf_dist};
     ga.Nu = h->d.turbulence == CMDG_TURB_SMAGORINSKY ? (R *)h->NuDev : nullptr;
     if ((rc = launch_gradient<R>(h, ga, nreal, st))) return rc;
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_TRACER_GRADIENT), st);
     tracer_gradient_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(ta, P);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_TRACER_GRADIENT), st);
     CU(cudaGetLastError());
     h->launches++;
     if (par) {
@@ -781,7 +789,9 @@ int eval_with_tracers(cmdg_handle h, void *dQ, const void *Q, void *Qout, double
   a.elems = nullptr;
   if (!write_diag) a.aux_out = nullptr;
   if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
+  if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_TRACER_TENDENCY), st);
   tracer_tendency_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>(ta, P);
+  if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_TRACER_TENDENCY), st);
   CU(cudaGetLastError());
   h->launches++;
   if (par && Qout) {

@@ -1160,6 +1160,15 @@ __device__ __forceinline__ void write_normal_flux(const R *__restrict__ sgeoP, R
 // onto its volume gradient and applies the gradient-flux map ONCE -- half the shared-memory traffic
 // of storing / re-reading 10 flux columns per face node (the kernel is LSU-bound like the tendency
 // kernel).  n . F2 at the element's own face nodes is written by the node threads too (no staging).
+// Round-2 experiment (profiles/r2_ncu_metrics_dg_gradient_*.csv, 61 440 elements, Held-Suarez): the plane-lane
+// contraction + warp specialisation of dg_tendency_kernel was ported to this kernel (one rotating warp
+// differentiates G plane by plane while three warps do the face items).  It cut the L1 data-pipe wavefronts
+// (106.9 M -> 95.9 M) and the instructions (379.6 M -> 363.8 M) but not the time: 1.358 M -> 1.386 M cycles.
+// Unlike the tendency kernel this one is not bound by the LSU pipe (L1 47-54 %, DRAM 44 %) but by latency at
+// 4.7 warps per scheduler and ~6000 warp instructions per element (theta_v = T (MSLP / p)^kappa at 225 points,
+// the Smagorinsky closure, n . F2 on up to three faces per node); serialising the contraction in one warp
+// lengthens the block's critical path by as much as the saved shared-memory traffic shortens it.  The per-node
+// contraction below therefore stays.
 template <class R, int NQ, bool AUX, bool HYPER>
 struct GradSmem {
   static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;

@@ -358,7 +358,8 @@ class DGModel:
     def kernel_class_ms(self):
         """Device ms and launch count per kernel class of the last fused-stepper call."""
         out = {}
-        for i, name in enumerate(("tendency", "gradient", "hyper_divergence", "hyper_flux")):
+        for i, name in enumerate(("tendency", "gradient", "hyper_divergence", "hyper_flux", "tracer_gradient",
+                                  "tracer_tendency", "hb_filter", "hb_column")):
             n = C.c_int64(0)
             ms = _lib.lib().cmdg_kernel_class_ms(self._h, i, C.byref(n))
             out[name] = (float(ms), int(n.value))

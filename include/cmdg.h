@@ -297,9 +297,11 @@ int64_t cmdg_kernel_launches(cmdg_handle h);
 int cmdg_set_timing(cmdg_handle h, int32_t enable);
 double cmdg_last_kernel_ms(cmdg_handle h, int64_t *nlaunches_out);
 /* The same split by kernel class: tendency (dg_tendency_kernel / hb_tendency_kernel), gradient pass
- * (dg_gradient_kernel), and the two DryBiharmonic passes. */
+ * (dg_gradient_kernel / hb_gradient_kernel), the two DryBiharmonic passes, the two passive-tracer kernels,
+ * and the HBModel's vertical filter and stack-integral (column) kernels. */
 enum { CMDG_KCLASS_TENDENCY = 0, CMDG_KCLASS_GRADIENT = 1, CMDG_KCLASS_HYPER_DIVERGENCE = 2,
-       CMDG_KCLASS_HYPER_FLUX = 3, CMDG_KCLASS_COUNT = 4 };
+       CMDG_KCLASS_HYPER_FLUX = 3, CMDG_KCLASS_TRACER_GRADIENT = 4, CMDG_KCLASS_TRACER_TENDENCY = 5,
+       CMDG_KCLASS_HB_FILTER = 6, CMDG_KCLASS_HB_COLUMN = 7, CMDG_KCLASS_COUNT = 8 };
 double cmdg_kernel_class_ms(cmdg_handle h, int32_t kclass, int64_t *nlaunches_out);
 
 #ifdef __cplusplus

@@ -7,8 +7,12 @@ the stream that does the work during the last two steps of a timed cmdg_lsrk_ste
 
 Columns (microseconds, last recorded step): for every stage the exterior chain on the side stream
 (exterior kernel, pack, wait for NCCL to start, NCCL send/recv, unpack) next to the interior kernel on
-the main stream, what the stage cost (from its first kernel start to the last of both chains) and how
-much of that the exterior chain stuck out beyond the interior kernel ("exposed")."""
+the main stream.  The two chains are only coupled through kernel-to-kernel events (interior(s+1) needs
+exterior-kernel(s), exterior-kernel(s+1) needs interior(s) and its own unpack(s)), so on a fast rank the
+interior chain runs up to one stage ahead of the exterior chain, which waits in NCCL for the slowest
+neighbour: `int_lead` = how far the interior kernel of the stage started before the exterior kernel,
+`int_gap` = idle time on the main stream between consecutive interior kernels (what a stage really costs
+beyond its interior kernel), `nccl` includes the wait for the neighbours."""
 import csv
 import glob
 import sys
@@ -40,8 +44,8 @@ def stage_row(marks):
     start = min(te0, ti0)
     end = max(ue, ti1)
     return dict(ext_kernel=te1 - te0, pack=pack - te1, nccl_wait=nb - pack, nccl=ne_ - nb, unpack_wait=ub - ne_,
-                unpack=ue - ub, ext_chain=ue - te0, interior=ti1 - ti0, int_start_after_ext=ti0 - te0,
-                stage=end - start, exposed=max(0.0, ue - ti1), start=start, end=end, n_ext=ie, n_int=ii)
+                unpack=ue - ub, ext_chain=ue - te0, interior=ti1 - ti0, int_lead=te0 - ti0,
+                start=start, end=end, n_ext=ie, n_int=ii, ti0=ti0, ti1=ti1, te0=te0, ue=ue)
 
 
 def main():
@@ -49,7 +53,7 @@ def main():
     files = sorted(glob.glob(prefix + ".rank*.csv"))
     print(f"# Stage timeline, {len(files)} rank(s), last recorded step (microseconds)\n")
     cols = ["ext_kernel", "pack", "nccl_wait", "nccl", "unpack_wait", "unpack", "ext_chain", "interior",
-            "int_start_after_ext", "stage", "exposed", "gap_to_next"]
+            "int_lead", "int_gap"]
     summary = []
     for f in files:
         rank = f.split(".rank")[-1].split(".")[0]
@@ -59,8 +63,8 @@ def main():
             print(f"rank {rank}: serial schedule / single rank (no exterior chain recorded)\n")
             continue
         for a, b in zip(rows, rows[1:]):
-            a["gap_to_next"] = b["start"] - a["end"]
-        rows[-1]["gap_to_next"] = float("nan")
+            a["int_gap"] = b["ti0"] - a["ti1"]
+        rows[-1]["int_gap"] = float("nan")
         print(f"## rank {rank}  (exterior {rows[0]['n_ext']} / interior {rows[0]['n_int']} elements)\n")
         print("| stage | " + " | ".join(cols) + " |")
         print("|---|" + "---|" * len(cols))
@@ -71,10 +75,10 @@ def main():
         summary.append((rank, tot))
     if summary:
         print("## per-rank sums over the 5 stages\n")
-        print("| rank | interior | ext_chain | exposed | gaps | stage total |")
+        print("| rank | interior kernels | gaps between them | exterior kernels | pack + unpack | nccl (incl. waiting for neighbours) |")
         print("|---|---|---|---|---|---|")
         for rank, t in summary:
-            print(f"| {rank} | {t['interior']:.1f} | {t['ext_chain']:.1f} | {t['exposed']:.1f} | {t['gap_to_next']:.1f} | {t['stage']:.1f} |")
+            print(f"| {rank} | {t['interior']:.1f} | {t['int_gap']:.1f} | {t['ext_kernel']:.1f} | {t['pack'] + t['unpack']:.1f} | {t['nccl']:.1f} |")
 
 
 if __name__ == "__main__":
