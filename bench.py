@@ -426,6 +426,33 @@ def secondary_run(P, args, workload, rank, world, dev, dist, steps, grid=None, s
     return out, host
 
 
+def bind_to_gpu_numa(local):
+    """One process per GPU: run on the cores that are local to this rank's GPU, so that the pinned host
+    buffers of the end-to-end leg (first touch) and the copy engines' DMA stay on the GPU's NUMA node.  Round 1
+    left every rank on the default policy and the 8-rank end-to-end step piled up on one socket's memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_cpus": len(cpus), "pci": bus}
+    except Exception as e:       # no NUMA information: keep the default placement
+        return {"numa_cpus": None, "why": str(e)[:80]}
+    return {"numa_cpus": None}
+
+
 def hbm_peak():
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
@@ -445,6 +472,7 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     args.keep_host_copy = False
@@ -600,7 +628,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(nodes_local * nstate * 8),
                 "d2h_bytes_per_step": int(nodes_local * nstate * 8),
                 "api": "cmdg_lsrk_steps_host (pinned host state in/out every step)",
-                "ms_per_step": e2e_s / e2e_steps * 1e3},
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "host_placement": numa},
         "gpu_launches": int(r["launches"]),
         "clocks": clk,
         "norm_ratio": r["norm_ratio"],
