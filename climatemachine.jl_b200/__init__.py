@@ -12,6 +12,6 @@ from .balance_laws import UnsupportedModelError
 from .dgmodel import (DGModel, DiscontinuousSpectralElementGrid, MPIStateArray,
                       LowStorageRungeKutta2N, LSRK54CarpenterKennedy,
                       LSRK144NiegemannDiehlBusch, solve, norm, euclidean_distance,
-                      comm_unique_id)
+                      comm_unique_id, ErrorOnRemoteNode)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -72,7 +72,7 @@ SYMBOLS = [
     "cmdg_lsrk_steps_host", "cmdg_comm_unique_id", "cmdg_comm_init", "cmdg_exchange_begin",
     "cmdg_exchange_end", "cmdg_sync", "cmdg_kernel_launches", "cmdg_set_timing",
     "cmdg_last_kernel_ms", "cmdg_kernel_class_ms", "cmdg_set_ocean_model", "cmdg_bind_ocean_operators",
-    "cmdg_filter_apply", "cmdg_set_step_filter", "cmdg_courant",
+    "cmdg_filter_apply", "cmdg_set_step_filter", "cmdg_courant", "cmdg_check_for_crashes",
 ]
 
 
@@ -106,6 +106,7 @@ def lib():
     L.cmdg_filter_apply.argtypes = [vp, vp, i32, i32, C.c_uint32, vp, vp, i32, vp]
     L.cmdg_set_step_filter.argtypes = [vp, i32, C.c_uint32, vp, vp, i32]
     L.cmdg_courant.argtypes = [vp, vp, vp, dbl, i32, i32, C.POINTER(dbl), vp]
+    L.cmdg_check_for_crashes.argtypes = [vp, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
     L.cmdg_comm_unique_id.argtypes = [vp]
     L.cmdg_comm_init.argtypes = [vp, vp, i32, i32]
     L.cmdg_exchange_begin.argtypes = [vp, vp, i32, vp]

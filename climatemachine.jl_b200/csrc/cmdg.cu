@@ -39,6 +39,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string &err) {
     if (lib) return true;
@@ -61,6 +62,7 @@ struct NcclApi {
     CMDG_SYM(GroupEnd, "ncclGroupEnd");
     CMDG_SYM(Send, "ncclSend");
     CMDG_SYM(Recv, "ncclRecv");
+    CMDG_SYM(AllReduce, "ncclAllReduce");
     CMDG_SYM(GetErrorString, "ncclGetErrorString");
 #undef CMDG_SYM
     return true;
@@ -95,6 +97,7 @@ struct cmdg_handle_s {
   size_t commbuf_states = 0;
   // per-step filter (cmdg_set_step_filter): row-major device copies of the two matrices
   void *courant_dev = nullptr;
+  int *crash_dev = nullptr;   // [2]: local flag, reduced flag (cmdg_check_for_crashes)
   void *stepWh = nullptr, *stepWv = nullptr, *tmpWh = nullptr, *tmpWv = nullptr;
   int step_filter_target = -1, step_filter_dir = 0;
   unsigned step_filter_mask = 0;
@@ -1299,7 +1302,7 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->crash_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
                   h->NuDev, h->F2chi};
   for (void *p : bufs)
     if (p) cudaFree(p);
@@ -1630,6 +1633,39 @@ int cmdg_exchange_end(cmdg_handle h, void *array, int32_t nstate, cmdg_stream st
   cudaStream_t st = (cudaStream_t)stream;
   return DISPATCH_FT(h, exchange_end_t<double>(h, array, nstate, st),
                      exchange_end_t<float>(h, array, nstate, st));
+}
+
+int cmdg_check_for_crashes(cmdg_handle h, const void *Q, int32_t nstate, int32_t *local_bad_host,
+                           int32_t *any_bad_host, cmdg_stream stream) {
+  if (!h || !Q || !local_bad_host || !any_bad_host || nstate <= 0)
+    return fail(h, CMDG_ERR_INVALID, "cmdg_check_for_crashes: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->crash_dev) CU(cudaMalloc((void **)&h->crash_dev, 2 * sizeof(int)));
+  CU(cudaMemsetAsync(h->crash_dev, 0, 2 * sizeof(int), st));
+  const size_t n = (size_t)h->d.nrealelem * nstate * h->Np;
+  if (n) {
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    if (h->fb == 8) nonfinite_kernel<double><<<blocks, 256, 0, st>>>((const double *)Q, n, h->crash_dev);
+    else nonfinite_kernel<float><<<blocks, 256, 0, st>>>((const float *)Q, n, h->crash_dev);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  if (h->comm) {
+    // one communicator, one stream at a time: the reduction goes on the halo stream, ordered after the scan
+    CU(cudaEventRecord(h->ev_ready, st));
+    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+    NC(g_nccl.AllReduce(h->crash_dev, h->crash_dev + 1, 1, ncclInt32, ncclMax, h->comm, h->comm_stream));
+    CU(cudaEventRecord(h->ev_done, h->comm_stream));
+    CU(cudaStreamWaitEvent(st, h->ev_done, 0));
+  } else {
+    CU(cudaMemcpyAsync(h->crash_dev + 1, h->crash_dev, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  int out[2] = {0, 0};
+  CU(cudaMemcpyAsync(out, h->crash_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *local_bad_host = out[0];
+  *any_bad_host = out[1];
+  return CMDG_OK;
 }
 
 int cmdg_sync(cmdg_handle h) {

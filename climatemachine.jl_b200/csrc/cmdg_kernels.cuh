@@ -1783,6 +1783,15 @@ __global__ void unpack_kernel(R *__restrict__ buf, const R *__restrict__ recvbuf
 }
 
 // Packed private geometry (built once in cmdg_bind_grid).
+// non-finite scan of realview(Q) (check_for_crashes, MPIStateArrays.jl:910-935)
+template <class R>
+__global__ void nonfinite_kernel(const R *__restrict__ x, size_t n, int *__restrict__ flag) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    bad |= !isfinite(x[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 //   vgeoP[e][c / 2][n][c % 2], c = 3*m + d : M * d(xi_{m+1})/d(x_{d+1});  c = 9 : MI
 //   (reference vgeo columns, Grids.jl:76-92: xi{m}x{d} at 3*(d-1)+(m-1), M = 9, MI = 10)
 template <class R>

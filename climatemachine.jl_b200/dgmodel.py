@@ -347,6 +347,20 @@ class DGModel:
                                            C.byref(out), st), self._h)
         return out.value
 
+    # -- check_for_crashes (MPIStateArrays.jl:910-935): NaN/Inf on this rank, and on any rank ------------
+    def check_for_crashes(self, Q, raise_on_failure=True):
+        """Returns (local_bad, any_bad).  With ``raise_on_failure`` a rank whose own state is not finite raises
+        ``FloatingPointError``; the other ranks raise ``ErrorOnRemoteNode`` as the reference does."""
+        lb, ab = C.c_int32(0), C.c_int32(0)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().cmdg_check_for_crashes(self._h, _ptr(Q.data), Q.nstate, C.byref(lb), C.byref(ab), st),
+                   self._h)
+        if raise_on_failure and lb.value:
+            raise FloatingPointError("non-finite values in the prognostic state on this rank")
+        if raise_on_failure and ab.value:
+            raise ErrorOnRemoteNode("another rank reported non-finite values")
+        return bool(lb.value), bool(ab.value)
+
     def set_timing(self, enable=True):
         _lib.check(_lib.lib().cmdg_set_timing(self._h, int(enable)), self._h)
 
@@ -378,6 +392,10 @@ class DGModel:
             self.close()
         except Exception:
             pass
+
+
+class ErrorOnRemoteNode(RuntimeError):
+    """``ErrorOnRemoteNode`` (src/Arrays/MPIStateArrays.jl:17)."""
 
 
 def comm_unique_id() -> bytes:

@@ -286,6 +286,17 @@ int cmdg_comm_init(cmdg_handle h, const void *id128_host, int32_t rank, int32_t 
 int cmdg_exchange_begin(cmdg_handle h, void *array, int32_t nstate, cmdg_stream stream);
 int cmdg_exchange_end(cmdg_handle h, void *array, int32_t nstate, cmdg_stream stream);
 
+/*
+ * Replaces the crash check of the reference's waits (`checked_wait` with `check_for_crashes`,
+ * src/Arrays/MPIStateArrays.jl:910-935, which raises `ErrorOnRemoteNode` on the ranks that did not fail
+ * themselves): counts the non-finite values in realview(Q) (Np x nstate x nrealelem) on this rank and, when a
+ * communicator was initialised, reduces the flag over all ranks (ncclAllReduce, max), so that EVERY rank
+ * learns that some rank holds NaN/Inf and can stop collectively instead of hanging in the next halo exchange.
+ * Synchronous.  *local_bad_host = 1 if this rank's state is not finite, *any_bad_host = 1 if any rank's is.
+ */
+int cmdg_check_for_crashes(cmdg_handle h, const void *Q, int32_t nstate, int32_t *local_bad_host,
+                           int32_t *any_bad_host, cmdg_stream stream);
+
 /* Blocks until all work queued by this handle has finished (checked_wait, DGModel.jl:426). */
 int cmdg_sync(cmdg_handle h);
 

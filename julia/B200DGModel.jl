@@ -453,4 +453,16 @@ function ghost_exchange!(b::B200DGModel, A::MPIStateArray)
     CUDA.synchronize()
 end
 
+# check_for_crashes of the reference's waits (MPIStateArrays.jl:910-935): NaN / Inf on this rank, and on any rank
+struct ErrorOnRemoteNodeB200 <: Exception end
+function check_for_crashes(b::B200DGModel, Q::MPIStateArray)
+    lb, ab = Ref{Int32}(0), Ref{Int32}(0)
+    check(b.handle, ccall((:cmdg_check_for_crashes, libcmdg), Cint,
+        (Ptr{Cvoid}, CuPtr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ptr{Cvoid}),
+        b.handle, pointer(Q.data), size(Q.data, 2), lb, ab, CUDA.stream().handle))
+    lb[] != 0 && error("B200DGModel: non-finite values in the prognostic state on this rank")
+    ab[] != 0 && throw(ErrorOnRemoteNodeB200())
+    return nothing
+end
+
 end # module

@@ -59,9 +59,47 @@ def main():
            for g, a in zip(gs, tmp.state_auxiliary)]
     run_case("baroclinic_wave_hyperdiffusion", model, gs, Q0s, "rusanov", 0.5, 2, rank, world, False, "horizontal")
     run_ocean(rank, world)
+    crash_propagation(rank, world)
     if world == 3:
         mpi_comm_known_answer(rank)
     dist.destroy_process_group()
+
+
+def crash_propagation(rank, world):
+    """check_for_crashes across ranks (MPIStateArrays.jl:910-935): a NaN on the LAST rank only is seen by every
+    rank (ncclAllReduce of the flag), the failing rank reports itself, the others 'ErrorOnRemoteNode'."""
+    P = parity.pkg()
+    model, gs, setup, dt = parity.vortex_setup((4, 4, 3), csize=world)
+    g = gs[rank]
+    odgm = odg.DGModel(model, gs, "rusanov", skip_zero_viscosity=True)
+    dgrid = parity.device_grid(g, device=f"cuda:{torch.cuda.current_device()}")
+    aux = P.MPIStateArray(dgrid, model.A, data=odgm.state_auxiliary[rank].data)
+    dg = P.DGModel(parity.device_model(model), dgrid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, skip_zero_viscosity=True)
+    uid = [P.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    dg.comm_init(uid[0], rank, world)
+    Q = P.MPIStateArray(dgrid, 5)
+    Q.data.fill_(1.0)
+    ok0 = dg.check_for_crashes(Q, raise_on_failure=False) == (False, False)
+    if rank == world - 1:
+        Q.data[0, 4, 5] = float("nan")
+    local, anyb = dg.check_for_crashes(Q, raise_on_failure=False)
+    ok = ok0 and anyb and (local == (rank == world - 1))
+    raised = None
+    try:
+        dg.check_for_crashes(Q)
+    except FloatingPointError:
+        raised = "local"
+    except P.ErrorOnRemoteNode:
+        raised = "remote"
+    ok = ok and raised == ("local" if rank == world - 1 else "remote")
+    flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"MULTI_GPU_PARITY crash_propagation world={world} ok={float(flag) == 0.0}", flush=True)
+    assert float(flag) == 0.0
+    dg.close()
 
 
 def mpi_comm_known_answer(rank):

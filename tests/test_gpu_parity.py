@@ -250,7 +250,7 @@ def test_multi_gpu_halo_and_parity(world):
          os.path.join(root, "tests", "multi_gpu_parity.py")],
         capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("MULTI_GPU_PARITY") == (6 if world == 3 else 5)
+    assert out.stdout.count("MULTI_GPU_PARITY") == (7 if world == 3 else 6)
 
 
 def test_ocean_hbmodel_tendency_and_steps():
@@ -406,3 +406,24 @@ def test_ocean_hbmodel_100_steps():
     """HBModel: 100 LSRK144 steps (1400 evaluations with filters, gradient pass, column scan, tendency)."""
     res = parity.ocean_case(nsteps=100, spinup=0)
     assert res["state_rel_l2"] <= TOL_STATE_F64, res
+
+
+def test_check_for_crashes_single_rank():
+    """cmdg_check_for_crashes (the reference's check_for_crashes waits, MPIStateArrays.jl:910-935): a finite
+    state passes, one NaN in a real element is reported, NaNs in ghost elements are not looked at."""
+    P = parity.pkg()
+    model, gs, setup, dt = parity.vortex_setup((3, 3, 2))
+    g = gs[0]
+    from oracle import dgmodel as odg
+    odgm = odg.DGModel(model, [g], "rusanov", skip_zero_viscosity=True)
+    dg, dgrid = parity.make_device_dg(odgm, g, "rusanov", skip_zero_viscosity=True)
+    Q = P.MPIStateArray(dgrid, 5)
+    Q.data.fill_(1.0)
+    assert dg.check_for_crashes(Q) == (False, False)
+    Q.data[3, 2, 17] = float("nan")
+    assert dg.check_for_crashes(Q, raise_on_failure=False) == (True, True)
+    with pytest.raises(FloatingPointError):
+        dg.check_for_crashes(Q)
+    Q.data[3, 2, 17] = float("inf")
+    assert dg.check_for_crashes(Q, raise_on_failure=False) == (True, True)
+    dg.close()
