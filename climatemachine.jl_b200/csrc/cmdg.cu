@@ -129,7 +129,7 @@ struct cmdg_handle_s {
   // Measured at 2 GPUs, LSRK54 steps/s: 331 (serial, normal-priority NCCL stream) -> 339 (high-priority
   // NCCL stream) -> 344 (+ this chain).
   cudaStream_t ext_stream = nullptr;
-  cudaEvent_t ev_ext = nullptr, ev_int = nullptr, ev_extk = nullptr;
+  cudaEvent_t ev_ext = nullptr, ev_int = nullptr, ev_extk = nullptr, ev_gextk = nullptr, ev_gint = nullptr;
   bool overlap_exterior = true;
   bool exchange_open = false;
   // bookkeeping
@@ -877,9 +877,17 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   // the ghosts unpacked by its own stream.  Per stage: max(interior, exterior + pack + NCCL + unpack).
   const bool overlap = par && !h->is_hb && !h->visc && !h->ntracers && h->step_filter_target < 0 && h->overlap_exterior &&
                        h->ext_stream && h->nexterior > 0 && h->ninterior > 0;
+  // Second-order path (no hyperdiffusion, no tracers): the same two chains with two halos per stage,
+  //   side stream:  grad_ext(s) -> [F2 halo] -> tend_ext(s) -> [Q halo] -> grad_ext(s+1) ...
+  //   main stream:  grad_int(s) ---------------> tend_int(s) -----------> grad_int(s+1) ...
+  // coupled kernel to kernel: tend_int(s) needs grad_ext(s) (Fn of its real neighbours), tend_ext(s) needs
+  // grad_int(s) and its own F2 unpack, grad_int(s+1) needs tend_ext(s), grad_ext(s+1) needs tend_int(s) and its
+  // own Q unpack.  (The reference overlaps the gradient-flux exchange with volume_tendency!, DGModel.jl:195-223.)
+  const bool overlap2 = par && !h->is_hb && h->visc && !h->hyper && !h->ntracers && h->step_filter_target < 0 &&
+                        h->overlap_exterior && h->ext_stream && h->nexterior > 0 && h->ninterior > 0;
   cudaStream_t xs = h->ext_stream;
   bool ext_pending = false;
-  if (overlap) {
+  if (overlap || overlap2) {
     if (int rc = ensure_const_D<R>(h, st)) return rc;
     CU(cudaEventRecord(h->ev_int, st));
     CU(cudaStreamWaitEvent(xs, h->ev_int, 0));
@@ -931,6 +939,35 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       const bool gf_needed = h->hyper && (h->d.turbulence == CMDG_TURB_SMAGORINSKY || h->d.turb_param != 0.0);
       if (s != nstage - 1 && !gf_needed) ga.gradflux = nullptr;
       int rc;
+      if (overlap2) {
+        const int64_t next = h->nexterior, ninr = h->ninterior;
+        ga.elems = h->exterior;
+        if ((rc = launch_gradient<R>(h, ga, next, xs))) return rc;
+        CU(cudaEventRecord(h->ev_gextk, xs));
+        if ((rc = exchange_begin_t<R>(h, h->F2dev, 12, xs))) return rc;
+        if ((rc = exchange_end_t<R>(h, h->F2dev, 12, xs))) return rc;
+        ga.elems = h->interior;
+        if ((rc = launch_gradient<R>(h, ga, ninr, st))) return rc;
+        CU(cudaEventRecord(h->ev_gint, st));
+        CU(cudaStreamWaitEvent(xs, h->ev_gint, 0));
+        a.elems = h->exterior;
+        if ((rc = launch_tendency<R>(h, a, next, xs))) return rc;
+        CU(cudaEventRecord(h->ev_extk, xs));
+        if ((rc = exchange_begin_t<R>(h, nxt, h->d.nstate, xs))) return rc;
+        if ((rc = exchange_end_t<R>(h, nxt, h->d.nstate, xs))) return rc;
+        CU(cudaEventRecord(h->ev_ext, xs));
+        CU(cudaStreamWaitEvent(st, h->ev_gextk, 0));
+        a.elems = h->interior;
+        if ((rc = launch_tendency<R>(h, a, ninr, st))) return rc;
+        CU(cudaEventRecord(h->ev_int, st));
+        CU(cudaStreamWaitEvent(xs, h->ev_int, 0));
+        CU(cudaStreamWaitEvent(st, h->ev_extk, 0));
+        ext_pending = true;
+        R *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        continue;
+      }
       // tail prefetch (Euler path): the last blocks of this stage's (last) launch warm L2 for the first
       // wave(s) of the next stage's launch(es): CMDG_TAILPF = number of elements per next launch (0 = off)
       const int tailpf = (h->visc || s == nstage - 1 && step + 1 == nsteps) ? 0 : h->tail_pf;
@@ -1288,6 +1325,8 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming);
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming);
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_extk, cudaEventDisableTiming);
+  if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_gextk, cudaEventDisableTiming);
+  if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_gint, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     delete h;
     return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
@@ -1314,6 +1353,8 @@ int cmdg_destroy(cmdg_handle h) {
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   if (h->ev_int) cudaEventDestroy(h->ev_int);
   if (h->ev_extk) cudaEventDestroy(h->ev_extk);
+  if (h->ev_gextk) cudaEventDestroy(h->ev_gextk);
+  if (h->ev_gint) cudaEventDestroy(h->ev_gint);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   delete h;
