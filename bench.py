@@ -488,9 +488,18 @@ def run_b200(args):
     nstate, nstage = (4, 14) if ocean else ((9, 14) if args.workload == "rising_bubble" else (5, 5))
     ne, nvert = default_mesh(args.workload, world, args)
     args.nvert = nvert
-    case = build_case(P, args.workload, ne, nvert, rank, world, dev, hyper=args.hyperdiffusion)
+    if args.emulate_rank:
+        er, ew = [int(x) for x in args.emulate_rank.split("/")]
+        ne = args.ne or WEAK_NE.get(ew, ne)
+        case = build_case(P, args.workload, ne, nvert, er, ew, dev, hyper=args.hyperdiffusion)
+    else:
+        case = build_case(P, args.workload, ne, nvert, rank, world, dev, hyper=args.hyperdiffusion)
     dg, grid = case["dg"], case["grid"]
     Q, sol = init_case(P, case, args.workload, rank, world, dist)
+    if args.emulate_rank:
+        ng = grid.nelem - grid.nrealelem
+        Q.data[grid.nrealelem:] = Q.data[:ng]
+        case["aux"].data[grid.nrealelem:] = case["aux"].data[:ng]
     nreal = grid.nrealelem
     nodes_local = nreal * NP
 
@@ -808,6 +817,8 @@ def main():
     ap.add_argument("--headline-only", action="store_true",
                     help="skip reference_schedule / secondary / sustained_100 (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--emulate-rank", default="", help="diagnostic: 'R/W' builds rank R of a W-rank partition on ONE GPU "
+                    "without a communicator (ghost elements hold copies of real ones)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that print to fd 1 (c10d's "NCCL version ..."
     # banner on the first communicator) are sent to stderr for the duration of the run

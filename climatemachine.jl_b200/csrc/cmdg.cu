@@ -13,6 +13,7 @@
 #include "cmdg_ocean.cuh"
 #include "cmdg_tracers.cuh"
 
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -69,6 +70,24 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
+
+// cuStreamWaitValue32 through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StreamWaitValue32Fn>(p);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
 
 }  // namespace
 
@@ -131,6 +150,12 @@ struct cmdg_handle_s {
   cudaStream_t ext_stream = nullptr;
   cudaEvent_t ev_ext = nullptr, ev_int = nullptr, ev_extk = nullptr, ev_gextk = nullptr, ev_gint = nullptr;
   bool overlap_exterior = true;
+  // single-launch schedule (CMDG_OVERLAP=2): launch list [exterior..., interior...], counter of finished exterior
+  // blocks (cumulative over stages), its running target on the host
+  int *all_list = nullptr;
+  unsigned *ext_done = nullptr;
+  unsigned ext_target = 0;
+  int overlap_mode = 2;
   bool exchange_open = false;
   // bookkeeping
   int64_t launches = 0;
@@ -885,6 +910,12 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   // own Q unpack.  (The reference overlaps the gradient-flux exchange with volume_tendency!, DGModel.jl:195-223.)
   const bool overlap2 = par && !h->is_hb && h->visc && !h->hyper && !h->ntracers && h->step_filter_target < 0 &&
                         h->overlap_exterior && h->ext_stream && h->nexterior > 0 && h->ninterior > 0;
+  // Euler path, single launch (CMDG_OVERLAP=2, default when the driver offers stream memory operations): ONE
+  // kernel per stage over [exterior..., interior...]; its exterior blocks count themselves done, the side stream
+  // waits for that count with cuStreamWaitValue32 and runs pack -> NCCL -> unpack while the same kernel goes on with
+  // the interior elements; the next stage's kernel waits for the unpack.  No small exterior launch (which costs about
+  // twice as much per element as the big one), no concurrent kernels competing for SM slots.
+  const bool overlap1 = overlap && h->overlap_mode >= 2 && h->all_list && h->ext_done && stream_wait_value32();
   cudaStream_t xs = h->ext_stream;
   bool ext_pending = false;
   if (overlap || overlap2) {
@@ -974,11 +1005,34 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
       a.pfn_Q = nxt;
       if (!par) {
         if (h->visc && (rc = second_order_passes<R>(h, ga, cur, false, true, false, st))) return rc;
-        a.elems = nullptr;
-        a.pfn_list[0] = nullptr;
+        // (diagnostic: CMDG_FORCE_LIST=1 runs a rank's launch list [exterior..., interior...] without a communicator)
+        static const bool force_list = getenv("CMDG_FORCE_LIST") != nullptr;
+        a.elems = (force_list && h->all_list) ? h->all_list : nullptr;
+        a.pfn_list[0] = a.elems;
         a.pfn_n[0] = (int)std::min<int64_t>(nreal, tailpf);
         if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
       } else {
+        if (overlap1) {
+          a.elems = h->all_list;
+          a.ext_done = h->ext_done;
+          a.n_signal = (int)h->nexterior;
+          a.pfn_list[0] = h->all_list;
+          a.pfn_n[0] = (int)std::min<int64_t>(nreal, tailpf);
+          if (ext_pending) CU(cudaStreamWaitEvent(st, h->ev_ext, 0));   // ghosts of this stage's input state
+          if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
+          h->ext_target += (unsigned)h->nexterior;
+          if (stream_wait_value32()((CUstream)xs, (CUdeviceptr)(uintptr_t)h->ext_done, h->ext_target,
+                                    CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail(h, CMDG_ERR_CUDA, "cuStreamWaitValue32 failed");
+          if ((rc = exchange_begin_t<R>(h, nxt, h->d.nstate, xs))) return rc;
+          if ((rc = exchange_end_t<R>(h, nxt, h->d.nstate, xs))) return rc;
+          CU(cudaEventRecord(h->ev_ext, xs));
+          ext_pending = true;
+          R *tmp = cur;
+          cur = nxt;
+          nxt = tmp;
+          continue;
+        }
         if (overlap) {
           a.elems = h->exterior;
           if ((rc = launch_tendency<R>(h, a, h->nexterior, xs))) return rc;
@@ -1310,7 +1364,10 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (const char *kv = getenv("CMDG_PF")) h->pf_dist = atoi(kv);
   if (const char *kv = getenv("CMDG_TAILPF")) h->tail_pf = atoi(kv);
   if (const char *kv = getenv("CMDG_TIMELINE")) h->tl_path = kv;
-  if (const char *kv = getenv("CMDG_OVERLAP")) h->overlap_exterior = atoi(kv) != 0;
+  if (const char *kv = getenv("CMDG_OVERLAP")) {
+    h->overlap_exterior = atoi(kv) != 0;
+    h->overlap_mode = atoi(kv);
+  }
   // the NCCL send/recv kernel is launched while the interior kernel still has thousands of blocks
   // queued: on a stream of the same priority its CTAs would be dispatched after them, i.e. the halo
   // would start when the interior kernel ends.  High priority puts them in front (CMDG_COMM_PRIO=0: off).
@@ -1341,7 +1398,8 @@ int cmdg_destroy(cmdg_handle h) {
   cudaDeviceSynchronize();
   void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
-                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->crash_dev, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
+                  h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->crash_dev,
+                  h->all_list, h->ext_done, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
                   h->NuDev, h->F2chi};
   for (void *p : bufs)
     if (p) cudaFree(p);
@@ -1383,6 +1441,14 @@ int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int6
   if ((rc = to_zero_based_list(h, exteriorelems, nexterior, &h->exterior))) return rc;
   h->ninterior = ninterior;
   h->nexterior = nexterior;
+  if (nexterior > 0 && ninterior > 0) {
+    // [exterior..., interior...] for the single-launch schedule + the counter its exterior blocks bump
+    CU(cudaMalloc((void **)&h->all_list, (size_t)(nexterior + ninterior) * sizeof(int)));
+    CU(cudaMemcpy(h->all_list, h->exterior, (size_t)nexterior * sizeof(int), cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(h->all_list + nexterior, h->interior, (size_t)ninterior * sizeof(int), cudaMemcpyDeviceToDevice));
+    CU(cudaMalloc((void **)&h->ext_done, sizeof(unsigned)));
+    CU(cudaMemset(h->ext_done, 0, sizeof(unsigned)));
+  }
   if ((rc = to_zero_based_map(h, vmapsend, nvmapsend, &h->vmapsend0))) return rc;
   if ((rc = to_zero_based_map(h, vmaprecv, nvmaprecv, &h->vmaprecv0))) return rc;
   h->nvmapsend = nvmapsend;

@@ -88,6 +88,12 @@ struct TendArgs {
   const int *pfn_list[2];
   int pfn_n[2];
   const R *pfn_Q;
+  // single-launch halo trigger: the first n_signal blocks of the launch (the exterior elements, listed first)
+  // bump *ext_done when their outputs are globally visible; a stream memory operation on the halo stream
+  // (cuStreamWaitValue32) waits for the count and then starts pack -> NCCL -> unpack while the same launch
+  // goes on with the interior elements
+  unsigned *ext_done;
+  int n_signal;
 };
 
 // conn.y layout: bits 0-2 neighbour face (0..5), bit 3 flip of first face index,
@@ -858,6 +864,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       A.dQ[eoffQ + (size_t)s * NP + tid] = d;
       if (A.Qout) A.Qout[eoffQ + (size_t)s * NP + tid] = q[s] + A.rkb_dt * d;
     }
+  }
+  if (A.ext_done != nullptr && (int)blockIdx.x < A.n_signal) {   // uniform per block
+    __threadfence();          // my stores (dQ, Qout) are visible device-wide ...
+    __syncthreads();          // ... for every thread of the block, before the block is counted
+    if (tid == 0) atomicAdd(A.ext_done, 1u);
   }
 #undef CMDG_ITEM
 }
