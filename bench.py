@@ -319,6 +319,12 @@ def time_steps(P, case, Q, sol, steps, warmup, world, dev, dist, clocks=None, ke
     l0 = dg.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if world > 1:
+        # the ranks leave the host barrier up to milliseconds apart, and a rank that starts early then waits for its
+        # neighbours inside the first halo -- with K = 20 that skew was 5 % of the timed region at 8 GPUs.  A
+        # stream-ordered all-reduce right before the start event aligns the DEVICE timelines of the ranks (the host
+        # barrier + synchronize on both sides of the timed region stay as they are).
+        dist.all_reduce(torch.zeros(1, device=dev))
     tc0 = time.perf_counter()
     e0.record()
     sol.dostep(Q, 0.0, nsteps=steps)
