@@ -621,7 +621,7 @@ def run_b200(args):
         "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "lsrk54_steps_per_s": args.steps / (ms * 1e-3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, ne, nvert, world),
                    "hyperdiffusion": ("DryBiharmonic(8 h), horizontal (3 extra kernels + 2 extra exchanges per evaluation)"
@@ -816,6 +816,9 @@ def main():
                     choices=["baroclinic_wave", "vortex", "ocean_gyre", "held_suarez", "rising_bubble"])
     ap.add_argument("--ne", type=int, default=0, help="horizontal elements per cube edge / box edge")
     ap.add_argument("--nvert", type=int, default=10)
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (SURVEY 10-3): the named mesh ne = 32 x 10 at every --gpus N instead of the "
+                         "weak-scaling series ne = 32 / 45 / 64 / 90")
     ap.add_argument("--hyperdiffusion", action="store_true",
                     help="baroclinic_wave / held_suarez as the reference's drivers ship them: DryBiharmonic(8 h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -826,6 +829,8 @@ def main():
     ap.add_argument("--emulate-rank", default="", help="diagnostic: 'R/W' builds rank R of a W-rank partition on ONE GPU "
                     "without a communicator (ghost elements hold copies of real ones)")
     args = ap.parse_args()
+    if args.strong and not args.ne:
+        args.ne = 32
     # stdout carries exactly one JSON line: libraries that print to fd 1 (c10d's "NCCL version ..."
     # banner on the first communicator) are sent to stderr for the duration of the run
     sys.stdout.flush()

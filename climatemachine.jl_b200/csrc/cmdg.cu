@@ -104,6 +104,10 @@ struct cmdg_handle_s {
   void *aux = nullptr, *gradflux = nullptr;
   // private device buffers
   void *vgeoP = nullptr, *sgeoP = nullptr, *Ddev = nullptr;
+  // plus-side geopotential / reference pressure per face node (constants of the grid; refreshed from the bound
+  // aux array by the first launch after cmdg_bind_state)
+  void *fauxP = nullptr;
+  bool faux_dirty = true;
   std::vector<double> Dhost;  // row-major D, mirrored into the constant-memory copy before launches
   int2 *conn = nullptr;
   int *interior = nullptr, *exterior = nullptr;
@@ -132,6 +136,22 @@ struct cmdg_handle_s {
   void *NuDev = nullptr, *F2chi = nullptr;
   void *Qtmp = nullptr;              // ping-pong partner of Q in cmdg_lsrk_steps
   void *Qdev = nullptr, *dQdev = nullptr;  // device state of cmdg_lsrk_steps_host
+  // Pipelined host path (cmdg_lsrk_steps_host; single rank, Euler path).  The upload is cut into element-range
+  // chunks on a copy stream and the first stage runs chunk by chunk over the elements whose stencil (the
+  // element and its face neighbours) has landed; the last stage runs range by range and every range goes back
+  // to the host while the next one is computed.  Only the first upload chunk's latency, the stragglers of the
+  // first stage and the last download chunk stay exposed.
+  struct HostPipe {
+    int nch = 0;
+    std::vector<int64_t> first;       // upload / download chunk c = elements [first[c], first[c+1])
+    std::vector<int64_t> ready_off;   // ready_list[ready_off[c] .. ready_off[c+1]) can run once chunk c has landed
+    int *ready_list = nullptr;        // device
+    int *identity = nullptr;          // device: 0 .. nreal-1 (range launches of the last stage)
+    cudaStream_t copy = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_k;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  } hp;
+  std::vector<int> nbr_host;         // [nreal][6] neighbour element of every face (-1: boundary face)
   bool grid_bound = false;
   // ocean (HBModel)
   bool is_hb = false, ocean_set = false;
@@ -149,6 +169,8 @@ struct cmdg_handle_s {
   // NCCL stream) -> 344 (+ this chain).
   cudaStream_t ext_stream = nullptr;
   cudaEvent_t ev_ext = nullptr, ev_int = nullptr, ev_extk = nullptr, ev_gextk = nullptr, ev_gint = nullptr;
+  cudaEvent_t ev_hb_fext = nullptr, ev_hb_fint = nullptr;   // ocean two-chain schedule: filters of the two chains
+  int *int_stacks = nullptr, *ext_stacks = nullptr;          // first element of every interior / exterior stack (HBModel)
   bool overlap_exterior = true;
   // single-launch schedule (CMDG_OVERLAP=2): launch list [exterior..., interior...], counter of finished exterior
   // blocks (cumulative over stages), its running target on the host
@@ -599,10 +621,12 @@ template <class R>
 int hb_launch_tend(cmdg_handle h, const HBArgs<R> &a, const HBParams<R> &P, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
   if (h->timing) cudaEventRecord(timing_event(h), st);
+  tl_mark(h, st, TL_KERNEL_BEGIN, 400000000LL + (long long)n);   // timeline info: kernel family * 1e8 + elements
   if (h->d.nf_first == CMDG_NF_RUSANOV)
     hb_tendency_kernel<R, 5, NF_RUSANOV><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
   else
     hb_tendency_kernel<R, 5, NF_CENTRAL><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(a, P);
+  tl_mark(h, st, TL_KERNEL_END, 400000000LL + (long long)n);
   if (h->timing) cudaEventRecord(timing_event(h), st);
   CU(cudaGetLastError());
   h->launches++;
@@ -611,7 +635,7 @@ int hb_launch_tend(cmdg_handle h, const HBArgs<R> &a, const HBParams<R> &P, int6
 
 template <class R>
 int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double beta,
-              double rkb_dt, cudaStream_t st) {
+              double rkb_dt, cudaStream_t st, bool two_chains = false) {
   const bool par = h->comm && !h->nabrtorank.empty();
   const int64_t nreal = h->d.nrealelem, nghost = h->d.nelem - nreal;
   const int nv = h->d.nvertelem;
@@ -630,66 +654,130 @@ int hb_eval_t(cmdg_handle h, void *dQ, void *Q, void *Qout, double alpha, double
   a.beta = (R)beta;
   a.rkb_dt = (R)rkb_dt;
   int rc;
-  auto grad = [&](const int *elems, int64_t n) -> int {
+  // timeline info of the marks: kernel family * 1e8 + elements
+  auto grad = [&](const int *elems, int64_t n, cudaStream_t s) -> int {
     if (n <= 0) return 0;
     HBArgs<R> g = a;
     g.elems = elems;
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
-    hb_gradient_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, st>>>(g, P);
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), st);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), s);
+    tl_mark(h, s, TL_KERNEL_BEGIN, 200000000LL + (long long)n);
+    hb_gradient_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, s>>>(g, P);
+    tl_mark(h, s, TL_KERNEL_END, 200000000LL + (long long)n);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_GRADIENT), s);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
   };
-  auto column = [&](int64_t elem0, int64_t nelems, int set_wz0) -> int {
+  // stacks [elem0, elem0 + nelems) or, with `stacks`, the listed ones (nelems = their element count)
+  auto column = [&](int64_t elem0, int64_t nelems, int set_wz0, const int *stacks, cudaStream_t s) -> int {
     if (nelems <= 0) return 0;
     // segmented scan (one block per stack, 32 element slots x 25 horizontal nodes) unless the stack is too
     // tall for the shared-memory carries or CMDG_HB_SERIAL_COLUMN asks for the reference-like serial march
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), st);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), s);
+    tl_mark(h, s, TL_KERNEL_BEGIN, 300000000LL + (long long)nelems);
     constexpr int SLOTS = 32;
     const size_t carry_bytes = (size_t)2 * nv * 25 * sizeof(R);
     static const bool serial = getenv("CMDG_HB_SERIAL_COLUMN") != nullptr;
     if (!serial && carry_bytes <= 40 * 1024) {
-      hb_column_scan_kernel<R, 5, SLOTS><<<(unsigned)(nelems / nv), SLOTS * 25, carry_bytes, st>>>(
+      hb_column_scan_kernel<R, 5, SLOTS><<<(unsigned)(nelems / nv), SLOTS * 25, carry_bytes, s>>>(
           (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
-          P.alphaT, nv, (int)elem0, set_wz0);
+          P.alphaT, nv, (int)elem0, set_wz0, stacks);
     } else {
-      hb_column_kernel<R, 5><<<(unsigned)(nelems / nv), 32, 0, st>>>(
+      hb_column_kernel<R, 5><<<(unsigned)(nelems / nv), 32, 0, s>>>(
           (R *)h->aux, (const R *)Q, (const R *)h->gradflux, (const R *)h->JcV, (const R *)h->Imat,
-          P.alphaT, nv, (int)elem0, set_wz0);
+          P.alphaT, nv, (int)elem0, set_wz0, stacks);
     }
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), st);
+    tl_mark(h, s, TL_KERNEL_END, 300000000LL + (long long)nelems);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_COLUMN), s);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
   };
-  // update_auxiliary_state!: vertical filters on the real elements, in place
+  // update_auxiliary_state!: vertical filters, in place
+  auto filter = [&](const int *elems, int64_t n, cudaStream_t s) -> int {
+    if (n <= 0) return 0;
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), s);
+    tl_mark(h, s, TL_KERNEL_BEGIN, 100000000LL + (long long)n);
+    hb_filter_kernel<R, 5><<<(unsigned)n, Dims<5>::BLOCK, 0, s>>>((R *)Q, (const R *)h->Fc, (const R *)h->Fe,
+                                                                  (int)nreal, elems);
+    tl_mark(h, s, TL_KERNEL_END, 100000000LL + (long long)n);
+    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), s);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+  };
+  auto tend = [&](const int *elems, int64_t n, cudaStream_t s) -> int {
+    HBArgs<R> t = a;
+    t.elems = elems;
+    return hb_launch_tend<R>(h, t, P, n, s);
+  };
+  if (par && two_chains) {
+    // Two chains coupled kernel to kernel (fused stepper, > 1 rank).  Whole stacks are interior or exterior, the
+    // vertical filters and the stack integrals never leave a stack, so every kernel family splits cleanly:
+    //   side stream (high priority): filter_ext -> [Q halo] -> grad_ext -> [GF halo || column_ext] -> column_ghost -> tend_ext
+    //   main stream:                 filter_int ------------> grad_int -> column_int ----------------------------> tend_int
+    // grad_x needs both filters, tend_x needs both gradients + column integrals; the main stream never waits for
+    // NCCL itself, only for exterior KERNELS.  Stage s + 1 is ordered behind stage s through the filters: filter_x(s+1)
+    // follows tend_x(s) in stream order, and every kernel that overwrites data the other chain's tend(s) reads
+    // (GF, aux.w / pkin / wz0, the ping-pong state) first waits for the other chain's filter(s+1).
+    cudaStream_t xs = h->ext_stream;
+    if ((rc = filter(h->exterior, h->nexterior, xs))) return rc;
+    CU(cudaEventRecord(h->ev_hb_fext, xs));
+    if ((rc = filter(h->interior, h->ninterior, st))) return rc;
+    CU(cudaEventRecord(h->ev_hb_fint, st));
+    if ((rc = exchange_begin_t<R>(h, Q, HB_S, xs))) return rc;
+    if ((rc = exchange_end_t<R>(h, Q, HB_S, xs))) return rc;
+    CU(cudaStreamWaitEvent(xs, h->ev_hb_fint, 0));
+    if ((rc = grad(h->exterior, h->nexterior, xs))) return rc;
+    if ((rc = exchange_begin_t<R>(h, h->gradflux, HB_GF, xs))) return rc;
+    if ((rc = column(0, h->nexterior, 1, h->ext_stacks, xs))) return rc;
+    CU(cudaEventRecord(h->ev_gextk, xs));
+    CU(cudaStreamWaitEvent(st, h->ev_hb_fext, 0));
+    if ((rc = grad(h->interior, h->ninterior, st))) return rc;
+    if ((rc = column(0, h->ninterior, 1, h->int_stacks, st))) return rc;
+    CU(cudaEventRecord(h->ev_gint, st));
+    if ((rc = exchange_end_t<R>(h, h->gradflux, HB_GF, xs))) return rc;
+    if ((rc = column(nreal, nghost, 0, nullptr, xs))) return rc;
+    CU(cudaStreamWaitEvent(xs, h->ev_gint, 0));
+    if ((rc = tend(h->exterior, h->nexterior, xs))) return rc;
+    CU(cudaEventRecord(h->ev_ext, xs));
+    CU(cudaStreamWaitEvent(st, h->ev_gextk, 0));
+    return tend(h->interior, h->ninterior, st);
+  }
+  if ((rc = filter(nullptr, nreal, st))) return rc;
+  if (!par) {
+    if ((rc = grad(nullptr, nreal, st))) return rc;
+    if ((rc = column(0, nreal, 1, nullptr, st))) return rc;
+    return tend(nullptr, nreal, st);
+  }
+  if ((rc = exchange_begin_t<R>(h, Q, HB_S, st))) return rc;
+  if ((rc = grad(h->interior, h->ninterior, st))) return rc;
+  if ((rc = exchange_end_t<R>(h, Q, HB_S, st))) return rc;
+  if ((rc = grad(h->exterior, h->nexterior, st))) return rc;
+  if ((rc = exchange_begin_t<R>(h, h->gradflux, HB_GF, st))) return rc;
+  if ((rc = column(0, nreal, 1, nullptr, st))) return rc;
+  if ((rc = tend(h->interior, h->ninterior, st))) return rc;
+  if ((rc = exchange_end_t<R>(h, h->gradflux, HB_GF, st))) return rc;
+  if ((rc = column(nreal, nghost, 0, nullptr, st))) return rc;
+  return tend(h->exterior, h->nexterior, st);
+}
+
+// (Re)build the packed plus-side aux constants on `st`, before the first launch that reads them.  Callers
+// invoke it on the stream every other stream of the schedule is ordered after.
+template <class R>
+int ensure_face_aux(cmdg_handle h, cudaStream_t st) {
+  if (!CMDG_FACE_AUX || !h->aux_model || h->is_hb || !h->faux_dirty) return 0;
+  const int64_t nreal = h->d.nrealelem;
+  if (!h->fauxP) CU(cudaMalloc(&h->fauxP, (size_t)nreal * 6 * h->Nfp * 2 * sizeof(R) + 16));
+  const AtmosParams<R> P = make_params<R>(h);
   if (nreal > 0) {
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), st);
-    hb_filter_kernel<R, 5><<<(unsigned)nreal, Dims<5>::BLOCK, 0, st>>>((R *)Q, (const R *)h->Fc,
-                                                                       (const R *)h->Fe, (int)nreal);
-    if (h->timing) cudaEventRecord(timing_event(h, CMDG_KCLASS_HB_FILTER), st);
+    pack_face_aux_kernel<R, 5><<<(unsigned)nreal, 160, 0, st>>>((const R *)h->aux, h->conn, P.naux, P.a_Phi,
+                                                                P.a_ref_p, (R *)h->fauxP);
     CU(cudaGetLastError());
     h->launches++;
   }
-  if (!par) {
-    if ((rc = grad(nullptr, nreal))) return rc;
-    if ((rc = column(0, nreal, 1))) return rc;
-    a.elems = nullptr;
-    return hb_launch_tend<R>(h, a, P, nreal, st);
-  }
-  if ((rc = exchange_begin_t<R>(h, Q, HB_S, st))) return rc;
-  if ((rc = grad(h->interior, h->ninterior))) return rc;
-  if ((rc = exchange_end_t<R>(h, Q, HB_S, st))) return rc;
-  if ((rc = grad(h->exterior, h->nexterior))) return rc;
-  if ((rc = exchange_begin_t<R>(h, h->gradflux, HB_GF, st))) return rc;
-  if ((rc = column(0, nreal, 1))) return rc;
-  a.elems = h->interior;
-  if ((rc = hb_launch_tend<R>(h, a, P, h->ninterior, st))) return rc;
-  if ((rc = exchange_end_t<R>(h, h->gradflux, HB_GF, st))) return rc;
-  if ((rc = column(nreal, nghost, 0))) return rc;
-  a.elems = h->exterior;
-  return hb_launch_tend<R>(h, a, P, h->nexterior, st);
+  h->faux_dirty = false;
+  return 0;
 }
 
 template <class R>
@@ -700,6 +788,7 @@ TendArgs<R> base_args(cmdg_handle h) {
   a.vgeoP = (const R *)h->vgeoP;
   a.sgeoP = (const R *)h->sgeoP;
   a.conn = h->conn;
+  a.fauxP = (const R *)h->fauxP;
   a.D = (const R *)h->Ddev;
   a.aux_out = h->d.write_aux_diagnostics ? (R *)h->aux : nullptr;
   a.pf_dist = h->pf_dist;
@@ -721,6 +810,7 @@ template <class R>
 int tendency_t(cmdg_handle h, void *dQ, void *Q, double t, double alpha, double beta,
                cudaStream_t st) {
   if (h->is_hb) return hb_eval_t<R>(h, dQ, Q, nullptr, alpha, beta, 0.0, st);
+  if (int rc0 = ensure_face_aux<R>(h, st)) return rc0;
   if (h->ntracers) return eval_with_tracers<R>(h, dQ, Q, nullptr, alpha, beta, 0.0, t, true, true, st);
   const bool par = h->comm && !h->nabrtorank.empty();
   const int64_t nreal = h->d.nrealelem;
@@ -883,11 +973,13 @@ int transpose_small(cmdg_handle h, const void *src_dev, int n, void **dst_dev) {
 template <class R>
 int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nstage,
                  const double *rka, const double *rkb, const double *rkc, int64_t nsteps,
-                 cudaStream_t st) {
+                 cudaStream_t st, void *host_Q = nullptr) {
+  // host_Q != NULL: pipelined host path (cmdg_lsrk_steps_host has enqueued the chunked upload on h->hp.copy)
   const bool par = h->comm && !h->nabrtorank.empty();
   const int64_t nreal = h->d.nrealelem;
   const size_t bytes = (size_t)h->d.nelem * h->d.nstate * h->Np * sizeof(R);
   if (!h->Qtmp) CU(cudaMalloc(&h->Qtmp, bytes));
+  if (int rc0 = ensure_face_aux<R>(h, st)) return rc0;
   R *cur = (R *)Q, *nxt = (R *)h->Qtmp;
   if (par && !h->is_hb) {
     // ghosts of the initial state
@@ -916,9 +1008,12 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   // the interior elements; the next stage's kernel waits for the unpack.  No small exterior launch (which costs about
   // twice as much per element as the big one), no concurrent kernels competing for SM slots.
   const bool overlap1 = overlap && h->overlap_mode >= 2 && h->all_list && h->ext_done && stream_wait_value32();
+  // HBModel: two chains as well (hb_eval_t)
+  const bool overlap_hb = par && h->is_hb && h->overlap_exterior && h->ext_stream && h->int_stacks && h->ext_stacks &&
+                          h->step_filter_target < 0 && (h->d.nelem - nreal) % std::max(1, h->d.nvertelem) == 0;
   cudaStream_t xs = h->ext_stream;
   bool ext_pending = false;
-  if (overlap || overlap2) {
+  if (overlap || overlap2 || overlap_hb) {
     if (int rc = ensure_const_D<R>(h, st)) return rc;
     CU(cudaEventRecord(h->ev_int, st));
     CU(cudaStreamWaitEvent(xs, h->ev_int, 0));
@@ -933,8 +1028,9 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
     for (int s = 0; s < nstage; ++s) {
       h->tl_stage = s;
       if (h->is_hb) {
-        int rc = hb_eval_t<R>(h, dQ, cur, nxt, 1.0, rka[s], (double)((R)rkb[s] * (R)dt), st);
+        int rc = hb_eval_t<R>(h, dQ, cur, nxt, 1.0, rka[s], (double)((R)rkb[s] * (R)dt), st, overlap_hb);
         if (rc) return rc;
+        if (overlap_hb) ext_pending = true;
         // the vertical filters act on the stage state itself: the ghost layer of the new state is
         // refreshed by the next evaluation's exchange
         R *tmp2 = cur;
@@ -1010,7 +1106,38 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
         a.elems = (force_list && h->all_list) ? h->all_list : nullptr;
         a.pfn_list[0] = a.elems;
         a.pfn_n[0] = (int)std::min<int64_t>(nreal, tailpf);
-        if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
+        const bool pipe_first = host_Q && step == 0 && s == 0;
+        const bool pipe_last = host_Q && step + 1 == nsteps && s == nstage - 1;
+        if (pipe_first || pipe_last) {
+          // first stage of the call: chunk c of the launch list needs upload chunks 0..c; last stage: range by
+          // range, each range's new state goes back to the host while the next range is computed
+          cmdg_handle_s::HostPipe &hp = h->hp;
+          a.pfn_n[0] = 0;
+          const size_t esz = (size_t)h->d.nstate * h->Np;
+          for (int c = 0; c < hp.nch; ++c) {
+            int64_t n;
+            if (pipe_first) {
+              CU(cudaStreamWaitEvent(st, hp.ev_up[c], 0));
+              a.elems = hp.ready_list + hp.ready_off[c];
+              n = hp.ready_off[c + 1] - hp.ready_off[c];
+            } else {
+              a.elems = hp.identity + hp.first[c];
+              n = hp.first[c + 1] - hp.first[c];
+            }
+            if ((rc = launch_tendency<R>(h, a, n, st))) return rc;
+            if (pipe_last) {
+              CU(cudaEventRecord(hp.ev_k[c], st));
+              CU(cudaStreamWaitEvent(hp.copy, hp.ev_k[c], 0));
+              const size_t o = (size_t)hp.first[c] * esz;
+              CU(cudaMemcpyAsync((R *)host_Q + o, nxt + o, (size_t)n * esz * sizeof(R), cudaMemcpyDeviceToHost,
+                                 hp.copy));
+            }
+          }
+          if (pipe_last) {
+            CU(cudaEventRecord(hp.ev_end, hp.copy));
+            CU(cudaStreamWaitEvent(st, hp.ev_end, 0));
+          }
+        } else if ((rc = launch_tendency<R>(h, a, nreal, st))) return rc;
       } else {
         if (overlap1) {
           a.elems = h->all_list;
@@ -1087,7 +1214,8 @@ int lsrk_steps_t(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int nst
   h->tl_on = false;
   // the caller's stream sees the last halo (ghosts of the final state) as well
   if (ext_pending) CU(cudaStreamWaitEvent(st, h->ev_ext, 0));
-  if (cur != (R *)Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
+  // (pipelined host path: the new state has already gone to the host range by range)
+  if (cur != (R *)Q && !host_Q) CU(cudaMemcpyAsync(Q, cur, bytes, cudaMemcpyDeviceToDevice, st));
   // the reference leaves dQ scaled by RKA[1] after the last stage (:130-141)
   const size_t n = (size_t)nreal * h->d.nstate * h->Np;
   if (rka[0] == 0.0) {
@@ -1138,6 +1266,7 @@ int build_conn(cmdg_handle h, const int64_t *vmapM_dev, const int64_t *vmapP_dev
     }
   };
   std::vector<int2> conn((size_t)nreal * 6);
+  h->nbr_host.assign((size_t)nreal * 6, -1);
   for (int64_t e = 0; e < nreal; ++e)
     for (int f = 0; f < 6; ++f) {
       const int64_t *pm = &vM[((size_t)e * 6 + f) * NFP];
@@ -1168,6 +1297,7 @@ int build_conn(cmdg_handle h, const int64_t *vmapM_dev, const int64_t *vmapP_dev
         return fail(h, CMDG_ERR_UNSUPPORTED,
                     "vmap+ face is not a conforming tensor-product face (orientation 1 or 3)");
       conn[(size_t)e * 6 + f] = make_int2((int)ep, found);
+      h->nbr_host[(size_t)e * 6 + f] = (int)ep;
     }
   CU(cudaMalloc(&h->conn, conn.size() * sizeof(int2) + 16));
   CU(cudaMemcpy(h->conn, conn.data(), conn.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1286,9 +1416,24 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
     h->is_hb = true;
     h->visc = true;
     if (const char *kv = getenv("CMDG_TIMELINE")) h->tl_path = kv;
-    if (cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+    if (const char *kv = getenv("CMDG_OVERLAP")) h->overlap_exterior = atoi(kv) != 0;
+    // NCCL stream and the exterior chain of the two-chain schedule (hb_eval_t) at high priority, as for the
+    // atmosphere: their small kernels must get SM slots while the interior kernels have thousands of blocks queued
+    int plo = 0, phi = 0;
+    cudaDeviceGetStreamPriorityRange(&plo, &phi);
+    const bool two = h->overlap_exterior;
+    bool ok = cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, two ? phi : plo) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) == cudaSuccess;
+    if (ok && two)
+      ok = cudaStreamCreateWithPriority(&h->ext_stream, cudaStreamNonBlocking, phi) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_gextk, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_gint, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_hb_fext, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_hb_fint, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
       delete h;
       return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
     }
@@ -1384,6 +1529,8 @@ int cmdg_create(const cmdg_desc *d, cmdg_handle *out) {
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_extk, cudaEventDisableTiming);
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_gextk, cudaEventDisableTiming);
   if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_gint, cudaEventDisableTiming);
+  if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_hb_fext, cudaEventDisableTiming);
+  if (e3 == cudaSuccess) e3 = cudaEventCreateWithFlags(&h->ev_hb_fint, cudaEventDisableTiming);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     delete h;
     return fail(nullptr, CMDG_ERR_CUDA, "cannot create stream/events");
@@ -1396,13 +1543,20 @@ int cmdg_destroy(cmdg_handle h) {
   if (g_constD_owner == h) g_constD_owner = nullptr;
   if (!h) return CMDG_OK;
   cudaDeviceSynchronize();
-  void *bufs[] = {h->vgeoP, h->sgeoP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
+  void *bufs[] = {h->vgeoP, h->sgeoP, h->fauxP, h->Ddev, h->conn, h->interior, h->exterior, h->vmapsend0,
                   h->vmaprecv0, h->sendbuf, h->recvbuf, h->Qtmp, h->Qdev, h->dQdev,
                   h->Fc, h->Fe, h->Imat, h->JcV, h->stepWh, h->stepWv, h->tmpWh, h->tmpWv, h->courant_dev, h->crash_dev,
-                  h->all_list, h->ext_done, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
+                  h->all_list, h->ext_done, h->int_stacks, h->ext_stacks, h->F2dev, h->FnDev, h->Qhg, h->Qhd,
                   h->NuDev, h->F2chi};
   for (void *p : bufs)
     if (p) cudaFree(p);
+  if (h->hp.ready_list) cudaFree(h->hp.ready_list);
+  if (h->hp.identity) cudaFree(h->hp.identity);
+  if (h->hp.copy) cudaStreamDestroy(h->hp.copy);
+  for (cudaEvent_t e : h->hp.ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->hp.ev_k) cudaEventDestroy(e);
+  if (h->hp.ev_begin) cudaEventDestroy(h->hp.ev_begin);
+  if (h->hp.ev_end) cudaEventDestroy(h->hp.ev_end);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   for (auto &m : h->tl) cudaEventDestroy(m.ev);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -1413,6 +1567,8 @@ int cmdg_destroy(cmdg_handle h) {
   if (h->ev_extk) cudaEventDestroy(h->ev_extk);
   if (h->ev_gextk) cudaEventDestroy(h->ev_gextk);
   if (h->ev_gint) cudaEventDestroy(h->ev_gint);
+  if (h->ev_hb_fext) cudaEventDestroy(h->ev_hb_fext);
+  if (h->ev_hb_fint) cudaEventDestroy(h->ev_hb_fint);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   delete h;
@@ -1459,6 +1615,29 @@ int cmdg_bind_grid(cmdg_handle h, const void *vgeo, const void *sgeo, const int6
     h->sendrange.push_back(nabrtovmapsend[2 * n + 1]);
     h->recvrange.push_back(nabrtovmaprecv[2 * n] - 1);
     h->recvrange.push_back(nabrtovmaprecv[2 * n + 1]);
+  }
+  if (h->is_hb && nexterior > 0 && ninterior > 0 && h->d.nvertelem > 0) {
+    // two-chain ocean schedule: stacks are whole on a rank, so a stack is interior or exterior as a whole; list the
+    // first element of each (if the lists do not split by stacks the serial schedule is used)
+    const int nv = h->d.nvertelem;
+    auto stacks_of = [&](const int *dev_list, int64_t n, int **out) -> int {
+      std::vector<int> v((size_t)n), firsts;
+      CU(cudaMemcpy(v.data(), dev_list, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+      std::vector<char> in((size_t)h->d.nrealelem, 0);
+      for (int e : v) in[(size_t)e] = 1;
+      for (int e : v)
+        if (e % nv == 0) {
+          bool whole = e + nv <= (int)h->d.nrealelem;
+          for (int k = 0; whole && k < nv; ++k) whole = in[(size_t)e + k] != 0;
+          if (whole) firsts.push_back(e);
+        }
+      if ((int64_t)firsts.size() * nv != n) return 0;   // not whole stacks: *out stays NULL
+      CU(cudaMalloc((void **)out, firsts.size() * sizeof(int)));
+      CU(cudaMemcpy(*out, firsts.data(), firsts.size() * sizeof(int), cudaMemcpyHostToDevice));
+      return 0;
+    };
+    if ((rc = stacks_of(h->interior, ninterior, &h->int_stacks))) return rc;
+    if ((rc = stacks_of(h->exterior, nexterior, &h->ext_stacks))) return rc;
   }
   if (h->is_hb) {
     const size_t n = (size_t)h->d.nelem * h->Np;
@@ -1517,6 +1696,7 @@ int cmdg_bind_state(cmdg_handle h, void *aux, void *gradflux) {
     return fail(h, CMDG_ERR_INVALID, "state_gradient_flux is required unless skip_zero_viscosity applies");
   h->aux = aux;
   h->gradflux = gradflux;
+  h->faux_dirty = true;
   if (h->visc && !h->is_hb && !h->F2dev) {
     // private outputs of the gradient kernel (zeroed: ghost entries are read before the first exchange
     // only on single-rank runs that have no ghosts)
@@ -1584,6 +1764,57 @@ int cmdg_lsrk_steps(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int3
                      lsrk_steps_t<float>(h, Q, dQ, t0, dt, nstage, rka, rkb, rkc, nsteps, st));
 }
 
+// Chunk tables of the pipelined host path (once per handle): upload chunk of every element, the chunk that
+// completes its stencil (itself and its face neighbours), launch list ordered by that chunk.
+static int build_host_pipe(cmdg_handle h) {
+  cmdg_handle_s::HostPipe &hp = h->hp;
+  if (hp.nch) return 0;
+  const int64_t nreal = h->d.nrealelem;
+  int nch = 8;
+  if (const char *v = getenv("CMDG_HOST_CHUNKS")) nch = std::max(1, std::min(64, atoi(v)));
+  nch = (int)std::min<int64_t>(nch, nreal / 8);
+  if ((int64_t)h->nbr_host.size() != nreal * 6) return fail(h, CMDG_ERR_INVALID, "host pipeline: no connectivity");
+  std::vector<int64_t> first(nch + 1);
+  for (int c = 0; c <= nch; ++c) first[c] = nreal * c / nch;
+  std::vector<int> chunk_of((size_t)nreal), ready((size_t)nreal);
+  for (int c = 0; c < nch; ++c)
+    for (int64_t e = first[c]; e < first[c + 1]; ++e) chunk_of[(size_t)e] = c;
+  std::vector<int64_t> off(nch + 1, 0);
+  for (int64_t e = 0; e < nreal; ++e) {
+    int r = chunk_of[(size_t)e];
+    for (int f = 0; f < 6; ++f) {
+      const int nb = h->nbr_host[(size_t)e * 6 + f];
+      if (nb >= 0 && nb < nreal) r = std::max(r, chunk_of[(size_t)nb]);
+    }
+    ready[(size_t)e] = r;
+    off[r + 1]++;
+  }
+  for (int c = 0; c < nch; ++c) off[c + 1] += off[c];
+  std::vector<int> list((size_t)nreal), ident((size_t)nreal);
+  std::vector<int64_t> pos(off.begin(), off.end() - 1);
+  for (int64_t e = 0; e < nreal; ++e) {     // stable: the memory order is kept inside a chunk
+    list[(size_t)pos[ready[(size_t)e]]++] = (int)e;
+    ident[(size_t)e] = (int)e;
+  }
+  CU(cudaMalloc(&hp.ready_list, (size_t)nreal * sizeof(int)));
+  CU(cudaMalloc(&hp.identity, (size_t)nreal * sizeof(int)));
+  CU(cudaMemcpy(hp.ready_list, list.data(), (size_t)nreal * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(hp.identity, ident.data(), (size_t)nreal * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
+  hp.ev_up.resize(nch);
+  hp.ev_k.resize(nch);
+  for (int c = 0; c < nch; ++c) {
+    CU(cudaEventCreateWithFlags(&hp.ev_up[c], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&hp.ev_k[c], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&hp.ev_begin, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&hp.ev_end, cudaEventDisableTiming));
+  hp.first = first;
+  hp.ready_off = off;
+  hp.nch = nch;
+  return 0;
+}
+
 int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int32_t nstage,
                          const double *rka, const double *rkb, const double *rkc,
                          int64_t nsteps) {
@@ -1597,6 +1828,32 @@ int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int3
     CU(cudaMalloc(&h->dQdev, all));
     CU(cudaMemset(h->Qdev, 0, all));
     CU(cudaMemset(h->dQdev, 0, all));
+  }
+  // Single rank, Euler path: upload, first stage, last stage and download are pipelined chunk by chunk
+  // (CMDG_HOST_PIPE=0 restores copy -> steps -> copy).  The other paths need the whole state (ghost exchange,
+  // gradient pass, column integrals) before their first kernel and copy it in one piece.
+  static const bool pipe_on = !(getenv("CMDG_HOST_PIPE") && atoi(getenv("CMDG_HOST_PIPE")) == 0);
+  const bool par = h->comm && !h->nabrtorank.empty();
+  const bool piped = pipe_on && !par && !h->is_hb && !h->ntracers && !h->visc && h->step_filter_target < 0 &&
+                     nstage > 0 && nsteps > 0 && (int64_t)nstage * nsteps >= 2 && rka && rkb && rkc &&
+                     h->d.nrealelem >= 16 && h->d.nelem == h->d.nrealelem;
+  if (piped) {
+    if ((rc = build_host_pipe(h))) return rc;
+    cmdg_handle_s::HostPipe &hp = h->hp;
+    const size_t esz = (size_t)h->d.nstate * h->Np * h->fb;
+    CU(cudaEventRecord(hp.ev_begin, 0));              // earlier work on the state buffers is finished first
+    CU(cudaStreamWaitEvent(hp.copy, hp.ev_begin, 0));
+    for (int c = 0; c < hp.nch; ++c) {
+      const size_t o = (size_t)hp.first[c] * esz;
+      CU(cudaMemcpyAsync((char *)h->Qdev + o, (const char *)Q_host + o, (size_t)(hp.first[c + 1] - hp.first[c]) * esz,
+                         cudaMemcpyHostToDevice, hp.copy));
+      CU(cudaEventRecord(hp.ev_up[c], hp.copy));
+    }
+    rc = DISPATCH_FT(h, lsrk_steps_t<double>(h, h->Qdev, h->dQdev, t0, dt, nstage, rka, rkb, rkc, nsteps, 0, Q_host),
+                     lsrk_steps_t<float>(h, h->Qdev, h->dQdev, t0, dt, nstage, rka, rkb, rkc, nsteps, 0, Q_host));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(0));
+    return CMDG_OK;
   }
   CU(cudaMemcpyAsync(h->Qdev, Q_host, real, cudaMemcpyHostToDevice, 0));
   rc = cmdg_lsrk_steps(h, h->Qdev, h->dQdev, t0, dt, nstage, rka, rkb, rkc, nsteps, nullptr);

@@ -71,6 +71,7 @@ struct TendArgs {
   const R *vgeoP;      // [nreal][5][Np] pairs: M*xi{m}x{d} (m-major) c = 0..8, MI c = 9; pair p = (c 2p, c 2p+1)  (80 B per node)
   const R *sgeoP;      // [nreal][6*Nfp][4]  n1,n2,n3, sM*vMI         (32 B per face node)
   const int2 *conn;    // [nreal][6]  x = neighbour element (0-based), y = meta
+  const R *fauxP;      // [nreal][6*Nfp][2]  neighbour's geopotential and reference pressure at the matching node (16 B per face node)
   const int *elems;    // launch list (0-based element ids) or NULL for identity
   const R *D;          // [Nq][Nq] row-major copy of Julia's D (D[a][b] = D_julia[a+1,b+1])
   R alpha, beta;       // dQ = alpha*RHS + beta*dQ
@@ -113,6 +114,46 @@ __device__ __forceinline__ int face_to_vol(int f, int a, int b) {
     default: return a + NQ * (b + NQ * (NQ - 1));
   }
 }
+
+// Index tables for Nq = 5 (compile-time constants in global memory, read through L1 with lane-consecutive
+// indices).  The face-item decomposition (it -> face, face node, (a, b), minus-side volume node), the
+// neighbour-side volume node for every (neighbour face, flip) and a node's three face items were integer
+// div / mod by 5 and 25 plus a six-way switch, recomputed in every phase: 12-16 % of the tendency kernel's
+// instructions (ncu source counters, round 2).
+constexpr int f2v_host(int NQ, int f, int a, int b) {
+  return f == 0 ? NQ * (a + NQ * b)
+       : f == 1 ? (NQ - 1) + NQ * (a + NQ * b)
+       : f == 2 ? a + NQ * NQ * b
+       : f == 3 ? a + NQ * ((NQ - 1) + NQ * b)
+       : f == 4 ? a + NQ * b
+                : a + NQ * (b + NQ * (NQ - 1));
+}
+struct IndexTables5 {
+  unsigned item[150];          // vm | f << 8 | fn << 12
+  unsigned char vp[16][25];    // [neighbour face | flip << 3][fn] -> neighbour volume node
+  unsigned node[128];          // it1 | it2 << 8 | it3 << 16 (255 = the node is not on a face in that direction)
+};
+constexpr IndexTables5 make_index_tables5() {
+  IndexTables5 t{};
+  for (int it = 0; it < 150; ++it) {
+    const int f = it / 25, fn = it % 25;
+    t.item[it] = (unsigned)f2v_host(5, f, fn % 5, fn / 5) | ((unsigned)f << 8) | ((unsigned)fn << 12);
+  }
+  for (int m = 0; m < 16; ++m)
+    for (int fn = 0; fn < 25; ++fn) {
+      const int f = m & 7, a = (m & 8) ? 4 - fn % 5 : fn % 5;
+      t.vp[m][fn] = (unsigned char)(f < 6 ? f2v_host(5, f, a, fn / 5) : 0);
+    }
+  for (int n = 0; n < 128; ++n) {
+    const int i = n % 5, j = (n / 5) % 5, k = n / 25;
+    const int it1 = n >= 125 ? 255 : (i == 0 ? j + 5 * k : (i == 4 ? 25 + j + 5 * k : 255));
+    const int it2 = n >= 125 ? 255 : (j == 0 ? 50 + i + 5 * k : (j == 4 ? 75 + i + 5 * k : 255));
+    const int it3 = n >= 125 ? 255 : (k == 0 ? 100 + i + 5 * j : (k == 4 ? 125 + i + 5 * j : 255));
+    t.node[n] = (unsigned)it1 | ((unsigned)it2 << 8) | ((unsigned)it3 << 16);
+  }
+  return t;
+}
+__device__ const IndexTables5 d_tbl5 = make_index_tables5();
 
 template <class R> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
@@ -363,6 +404,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
+// Experiment, off by default (-DCMDG_FACE_AUX=1 builds it).  The plus-side geopotential and reference pressure of
+// a face node are constants of the grid (aux columns the model never changes after init): instead of gathering
+// them through L1 at every launch (2 of the 7 scattered 8-byte cp.async per face node plus their shared-memory
+// round trip) they can be read from a packed per-face-node copy, one coalesced 16-byte load (built by
+// pack_face_aux_kernel at the first launch after cmdg_bind_state).  Measured on one box (ncu, 61 440 elements,
+// profiles/r2_ncu_metrics_dg_tendency_face_aux*.csv): L1 data-pipe wavefronts 108.5 M -> 101.8 M (shared 76.2 M ->
+// 68.1 M), DRAM reads +6 %, 926 k -> 919 k cycles (-0.8 %); bench 68.6 -> 69.1 GDOF/s.  The Held-Suarez
+// instantiation (VISC, 124 registers) got SLOWER: 0.828 -> 0.871 ms per launch.  The kernel is past the point
+// where fewer LSU wavefronts buy time (L1 75 %, DRAM 69 %: latency at 5 blocks per SM), and a cached copy of
+// caller-owned aux columns is a semantic liability for a drop-in, so the gathers stay.
+#ifndef CMDG_FACE_AUX
+#define CMDG_FACE_AUX 0
+#endif
 template <class R, int NQ, bool AUX, bool VISC>
 struct TendSmem {
   static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
@@ -376,7 +430,7 @@ struct TendSmem {
   R Qp[5][NFN];                            // neighbour traces; reused for the face results
   R P[NP], Rinv[NP];                       // own pressure, 1/rho
   R Phi[AUX ? NP : 1], Pref[AUX ? NP : 1]; // own geopotential, reference pressure
-  R Ap[2][AUX ? NFN : 1];                  // neighbour geopotential, reference pressure
+  R Ap[2][(AUX && !CMDG_FACE_AUX) ? NFN : 1];   // neighbour geopotential, reference pressure (gather variant)
   alignas(16) R Fnp[VISC ? NFN : 1][4];    // neighbour's n+ . F2+ at my face items (16-byte cp.async)
 };
 
@@ -481,13 +535,19 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   // item of round r: dense (ft + r * FSTRIDE) or face-aligned ((fw + r (NWARP-1)) Nfp + lane)
 #define CMDG_ITEM(r) (FALIGN ? ((ft >= 0) ? (fw + (r) * (NWARP - 1)) * NFP + lane : NFN) : ft + (r) * FSTRIDE)
   int2 cn[NITEM];
+  unsigned ti[NITEM];   // item info from the index table: vm | f << 8 | fn << 12
+  static_assert(NQ == 5, "index tables are built for Nq = 5");
 #pragma unroll
   for (int r = 0; r < NITEM; ++r) {
     const int it = CMDG_ITEM(r);
-    cn[r] = (ft >= 0 && it < NFN) ? A.conn[(size_t)e * 6 + it / NFP] : make_int2(0, 0);
+    ti[r] = (ft >= 0 && it < NFN) ? d_tbl5.item[it] : 0u;
+    cn[r] = (ft >= 0 && it < NFN) ? A.conn[(size_t)e * 6 + ((ti[r] >> 8) & 15)] : make_int2(0, 0);
     // face geometry of my items is needed only in the face phase: park it in L1 now
-    if (ft >= 0 && it < NFN)
+    if (ft >= 0 && it < NFN) {
       asm volatile("prefetch.global.L1 [%0];" ::"l"(A.sgeoP + ((size_t)e * NFN + it) * 4));
+      if (AUX && CMDG_FACE_AUX)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.fauxP + ((size_t)e * NFN + it) * 2));
+    }
   }
 
   // ---- L2 prefetch for the block that will replace this one on the SM: the one-shot kernel
@@ -500,6 +560,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
     prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R));
     if (A.beta != R(0)) prefetch_l2_bulk(A.dQ + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
+    if (AUX && CMDG_FACE_AUX) prefetch_l2_bulk(A.fauxP + (size_t)en * NFN * 2, NFN * 2 * sizeof(R));
     if (AUX) {
       const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
       const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
@@ -525,6 +586,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       prefetch_l2_bulk(A.dQ + (size_t)en * P.nstate * NP, 5 * NP * sizeof(R));
       prefetch_l2_bulk(A.vgeoP + (size_t)en * NP * 10, NP * 10 * sizeof(R));
       prefetch_l2_bulk(A.sgeoP + (size_t)en * NFN * 4, NFN * 4 * sizeof(R));
+      if (AUX && CMDG_FACE_AUX) prefetch_l2_bulk(A.fauxP + (size_t)en * NFN * 2, NFN * 2 * sizeof(R));
       if (AUX) {
         const int lo = P.a_Phi >= 0 ? P.a_Phi : P.a_ref_rho;
         const int hi = P.a_ref_p >= 0 ? P.a_ref_p + 1 : P.a_gradPhi + 3;
@@ -574,23 +636,22 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   for (int r = 0; r < NITEM; ++r) {
     const int it = CMDG_ITEM(r);
     if (ft >= 0 && it < NFN && ((cn[r].y >> 4) & 15) == 0) {
-      const int fn = it % NFP;
-      int a = fn % NQ;
-      const int b = fn / NQ;
-      if (cn[r].y & 8) a = NQ - 1 - a;
-      const int vp = face_to_vol<NQ>(cn[r].y & 7, a, b);
+      const int fn = (int)(ti[r] >> 12);
+      const int vp = d_tbl5.vp[cn[r].y & 15][fn];
       const size_t offp = (size_t)cn[r].x * P.nstate * NP + vp;
 #pragma unroll
       for (int s = 0; s < 5; ++s) cp_async<sizeof(R)>(&S.Qp[s][it], Qg + offp + (size_t)s * NP);
-      if (AUX) {
+      if (AUX && !CMDG_FACE_AUX) {
         const size_t offa = (size_t)cn[r].x * P.naux * NP + vp;
-        if (P.a_Phi >= 0) cp_async<sizeof(R)>(&S.Ap[0][it], auxg + offa + (size_t)P.a_Phi * NP);
+        constexpr bool G = AUX && !CMDG_FACE_AUX;
+        if (P.a_Phi >= 0) cp_async<sizeof(R)>(&S.Ap[0][G ? it : 0], auxg + offa + (size_t)P.a_Phi * NP);
         if (P.a_ref_p >= 0)
-          cp_async<sizeof(R)>(&S.Ap[1][AUX ? it : 0], auxg + offa + (size_t)P.a_ref_p * NP);
+          cp_async<sizeof(R)>(&S.Ap[1][G ? it : 0], auxg + offa + (size_t)P.a_ref_p * NP);
       }
       if (VISC && cn[r].x < A.nreal) {
         // the neighbour's own normal diffusive flux at the matching face node (32 contiguous bytes)
-        const R *fnp = A.Fn + ((size_t)cn[r].x * NFN + (cn[r].y & 7) * NFP + a + NQ * b) * 4;
+        const int a = (cn[r].y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
+        const R *fnp = A.Fn + ((size_t)cn[r].x * NFN + (cn[r].y & 7) * NFP + a + NQ * (fn / NQ)) * 4;
         cp_async<2 * sizeof(R)>(&S.Fnp[VISC ? it : 0][0], fnp);
         cp_async<2 * sizeof(R)>(&S.Fnp[VISC ? it : 0][2], fnp + 2);
       }
@@ -675,7 +736,6 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   // operand), only xi3 reads the other planes: 7 shared loads per output instead of 18.  The
   // tendency kernel is bound by the LSU data pipe, so this -- not the flops -- is what counts.
   // The result replaces the F[0] plane the lane has just consumed.
-  const int i = tid % NQ, j = (tid / NQ) % NQ, k = tid / (NQ * NQ);
   if (warp == cw) {
     if (lane < NQ * 5) {
       // (1) lane = (k-plane pk, state ps): xi1 and xi2, result in place of the F12[0] plane
@@ -737,12 +797,16 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   for (int r = 0; r < NITEM; ++r) {
     const int it = CMDG_ITEM(r);
     if (it >= NFN) break;
-    const int f = it / NFP, fn = it - f * NFP;
+    const int fn = (int)(ti[r] >> 12);
     const int2 c = cn[r];
     const int bctag = (c.y >> 4) & 15;
-    const int vm = face_to_vol<NQ>(f, fn % NQ, fn / NQ);
+    const int vm = (int)(ti[r] & 255u);
     R n[3], sMvMI;
     load_sgeo<R>(A.sgeoP + ((size_t)e * NFN + it) * 4, n, sMvMI);
+    typename Vec2<R>::type fa;
+    fa.x = fa.y = R(0);
+    if (AUX && CMDG_FACE_AUX)
+      fa = *reinterpret_cast<const typename Vec2<R>::type *>(A.fauxP + ((size_t)e * NFN + it) * 2);
     // second-order path: my own normal diffusive flux n . F2- (gradient kernel), loaded early
     typename Vec2<R>::type fnm0, fnm1;
     fnm0.x = fnm0.y = fnm1.x = fnm1.y = R(0);
@@ -765,9 +829,13 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     if (bctag == 0) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) qp[s] = S.Qp[s][it];
-      if (AUX) {
-        if (P.a_Phi >= 0) Phip = S.Ap[0][AUX ? it : 0];
-        if (P.a_ref_p >= 0) prefp = S.Ap[1][AUX ? it : 0];
+      if (AUX && CMDG_FACE_AUX) {
+        if (P.a_Phi >= 0) Phip = fa.x;
+        if (P.a_ref_p >= 0) prefp = fa.y;
+      } else if (AUX) {
+        constexpr bool G = AUX && !CMDG_FACE_AUX;
+        if (P.a_Phi >= 0) Phip = S.Ap[0][G ? it : 0];
+        if (P.a_ref_p >= 0) prefp = S.Ap[1][G ? it : 0];
       }
     } else {
       // boundary_state! (src/Atmos/Model/bc_momentum.jl:24-33, 60-70)
@@ -818,8 +886,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
         for (int s = 0; s < 4; ++s) fnp[s] = -S.Fnp[VISC ? it : 0][s];
       } else {
         // ghost neighbour: its F2 arrived by the halo exchange, contract with my normal
-        const int a2 = (c.y & 8) ? NQ - 1 - fn % NQ : fn % NQ;
-        const int vp = face_to_vol<NQ>(c.y & 7, a2, fn / NQ);
+        const int vp = d_tbl5.vp[c.y & 15][fn];
         const R *pg = A.F2 + (size_t)c.x * 12 * NP + vp;
 #pragma unroll
         for (int s = 0; s < 4; ++s)
@@ -843,18 +910,17 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) acc[s] = MI * (S.F12[0][s][tid] + S.F3[s][tid]) + src[s];
     // a node lies on at most one face per direction: three predicated reads instead of six
-    const int it1 = (i == 0) ? j + NQ * k : ((i == NQ - 1) ? NFP + j + NQ * k : -1);
-    const int it2 = (j == 0) ? 2 * NFP + i + NQ * k : ((j == NQ - 1) ? 3 * NFP + i + NQ * k : -1);
-    const int it3 = (k == 0) ? 4 * NFP + i + NQ * j : ((k == NQ - 1) ? 5 * NFP + i + NQ * j : -1);
-    if (it1 >= 0) {
+    const unsigned nt = d_tbl5.node[tid];
+    const int it1 = (int)(nt & 255u), it2 = (int)((nt >> 8) & 255u), it3 = (int)((nt >> 16) & 255u);
+    if (it1 != 255) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it1];
     }
-    if (it2 >= 0) {
+    if (it2 != 255) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it2];
     }
-    if (it3 >= 0) {
+    if (it3 != 255) {
 #pragma unroll
       for (int s = 0; s < 5; ++s) acc[s] -= S.Qp[s][it3];
     }
@@ -871,6 +937,29 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     if (tid == 0) atomicAdd(A.ext_done, 1u);
   }
 #undef CMDG_ITEM
+}
+
+// Packed plus-side aux constants of every face node (see CMDG_FACE_AUX): one block per real element.
+template <class R, int NQ>
+__global__ void __launch_bounds__(Dims<NQ>::NFN <= 160 ? 160 : 1024)
+pack_face_aux_kernel(const R *__restrict__ aux, const int2 *__restrict__ conn, int naux, int a_Phi, int a_ref_p,
+                     R *__restrict__ fauxP) {
+  constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
+  static_assert(NQ == 5, "index tables are built for Nq = 5");
+  const int e = blockIdx.x;
+  for (int it = threadIdx.x; it < NFN; it += blockDim.x) {
+    const unsigned ti = d_tbl5.item[it];
+    const int2 c = conn[(size_t)e * 6 + ((ti >> 8) & 15)];
+    R phi = R(0), pref = R(0);
+    if (((c.y >> 4) & 15) == 0) {
+      const int vp = d_tbl5.vp[c.y & 15][ti >> 12];
+      const size_t offa = (size_t)c.x * naux * NP + vp;
+      if (a_Phi >= 0) phi = aux[offa + (size_t)a_Phi * NP];
+      if (a_ref_p >= 0) pref = aux[offa + (size_t)a_ref_p * NP];
+    }
+    fauxP[((size_t)e * NFN + it) * 2] = phi;
+    fauxP[((size_t)e * NFN + it) * 2 + 1] = pref;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -68,11 +68,12 @@ __device__ __forceinline__ void hb_gradient_flux(const HBParams<R> &P, const R d
 // ---------------------------------------------------------------------------------------
 template <class R, int NQ>
 __global__ void __launch_bounds__(Dims<NQ>::BLOCK)
-hb_filter_kernel(R *__restrict__ Q, const R *__restrict__ Fc, const R *__restrict__ Fe, int nreal) {
+hb_filter_kernel(R *__restrict__ Q, const R *__restrict__ Fc, const R *__restrict__ Fe, int nreal,
+                 const int *__restrict__ elems) {
   constexpr int NP = Dims<NQ>::NP;
   __shared__ R s[3][NP];
   __shared__ R sF[2][NQ * NQ];
-  const int tid = threadIdx.x, e = blockIdx.x;
+  const int tid = threadIdx.x, e = elems ? elems[blockIdx.x] : blockIdx.x;   // launch list or identity
   if (tid < NQ * NQ) {
     sF[0][tid] = Fc[tid];
     sF[1][tid] = Fe[tid];
@@ -232,14 +233,15 @@ template <class R, int NQ>
 __global__ void hb_column_kernel(R *__restrict__ aux, const R *__restrict__ Q,
                                  const R *__restrict__ gradflux, const R *__restrict__ JcV,
                                  const R *__restrict__ Imat, R alphaT, int nvert, int elem0,
-                                 int set_wz0) {
+                                 int set_wz0, const int *__restrict__ stack_first) {
   constexpr int NP = Dims<NQ>::NP, NQH = NQ * NQ;
   __shared__ R sI[NQ * NQ];
   const int ij = threadIdx.x;
   if (ij < NQ * NQ) sI[ij] = Imat[ij];
   __syncthreads();
   if (ij >= NQH) return;
-  const int e0 = elem0 + blockIdx.x * nvert;
+  // stacks elem0, elem0 + nvert, ... or the listed stacks (first element of each)
+  const int e0 = stack_first ? stack_first[blockIdx.x] : elem0 + blockIdx.x * nvert;
   R cw = 0, cp = 0;  // carried integrals (top value of the element below)
   for (int ev = 0; ev < nvert; ++ev) {
     const size_t e = (size_t)(e0 + ev);
@@ -291,7 +293,7 @@ template <class R, int NQ, int SLOTS>
 __global__ void __launch_bounds__(SLOTS * NQ * NQ)
 hb_column_scan_kernel(R *__restrict__ aux, const R *__restrict__ Q, const R *__restrict__ gradflux,
                       const R *__restrict__ JcV, const R *__restrict__ Imat, R alphaT, int nvert, int elem0,
-                      int set_wz0) {
+                      int set_wz0, const int *__restrict__ stack_first) {
   constexpr int NP = Dims<NQ>::NP, NQH = NQ * NQ;
   extern __shared__ __align__(16) unsigned char hb_col_smem[];
   R *topw = reinterpret_cast<R *>(hb_col_smem);     // [nvert][NQH]
@@ -301,7 +303,7 @@ hb_column_scan_kernel(R *__restrict__ aux, const R *__restrict__ Q, const R *__r
   const int tid = threadIdx.x;
   const int ij = tid % NQH, slot = tid / NQH;
   if (tid < NQ * NQ) sI[tid] = Imat[tid];
-  const int e0 = elem0 + blockIdx.x * nvert;
+  const int e0 = stack_first ? stack_first[blockIdx.x] : elem0 + blockIdx.x * nvert;
   __syncthreads();
   // pass 1: element tops (row Nq-1 of Imat applied to the integrands)
   for (int ev = slot; ev < nvert; ev += SLOTS) {

@@ -227,7 +227,10 @@ int cmdg_lsrk_steps(cmdg_handle h, void *Q, void *dQ, double t0, double dt, int3
 /*
  * Same as cmdg_lsrk_steps but through HOST buffers: copies realview(Q) (Np*nstate*nrealelem
  * values) from Q_host to the device, runs nsteps steps, copies the result back and
- * synchronises.  This is the call the end-to-end benchmark times.
+ * synchronises.  This is the call the end-to-end benchmark times.  Q_host should be pinned
+ * (cudaHostAlloc / cudaHostRegister); pageable memory works but serialises the copies.  On one rank
+ * the Euler path overlaps the upload with the first stage and the download with the last one
+ * (chunked copies on a private stream, bit-identical results; CMDG_HOST_PIPE=0 turns it off).
  */
 int cmdg_lsrk_steps_host(cmdg_handle h, void *Q_host, double t0, double dt, int32_t nstage,
                          const double *rka_host, const double *rkb_host,

@@ -92,6 +92,7 @@ def compare_case(model, g, Q0, nf="rusanov", nsteps=1, dt=None, diffusion_direct
     oQ = omsa.MPIStateArray.from_grid(g, 5)
     np.moveaxis(oQ.data[:g.nreal], 1, 0)[...] = Q0
     omsa.ghost_exchange([oQ])
+    oQ0_data = oQ.data.copy()
     dg, dgrid = make_device_dg(odgm, g, nf, diffusion_direction, skip_zero_viscosity)
     dQ = P.MPIStateArray(dgrid, 5, data=oQ.data)
     # (i) tendency, beta = 0
@@ -125,6 +126,19 @@ def compare_case(model, g, Q0, nf="rusanov", nsteps=1, dt=None, diffusion_direct
         if nsteps <= 2:
             res["state_unfused_rel_l2"] = rel_l2(dQ2.realdata.cpu().numpy(), oQ.realdata)
         res["dQ_after_step_max"] = float(dsol.dQ.realdata.abs().max())
+        # the same steps through HOST buffers (cmdg_lsrk_steps_host; on one rank the Euler path pipelines the
+        # upload with the first stage and the download with the last one): bit-identical to the resident path
+        import torch
+        Qh = torch.from_numpy(np.ascontiguousarray(oQ0_data[:g.nreal])).pin_memory()
+        dsol3 = P.LSRK54CarpenterKennedy(dg, dQ, dt=dt, t0=t)
+        k = min(nsteps, 3)
+        for i in range(k):      # one call per step, as a host-side time loop does
+            dsol3.dostep_host(Qh, t + i * dt, nsteps=1)
+        Qd = P.MPIStateArray(dgrid, 5, data=oQ0_data)
+        dsol4 = P.LSRK54CarpenterKennedy(dg, Qd, dt=dt, t0=t)
+        P.solve(Qd, dsol4, numberofsteps=k)
+        res["host_path_max_abs_diff"] = float((Qh - Qd.realdata.cpu()).abs().max())
+        assert res["host_path_max_abs_diff"] == 0.0, res["host_path_max_abs_diff"]
     res["launches"] = dg.kernel_launches()
     dg.close()
     return res
