@@ -433,9 +433,13 @@ def secondary_run(P, args, workload, rank, world, dev, dist, steps, grid=None, s
 
 
 def bind_to_gpu_numa(local):
-    """One process per GPU: run on the cores that are local to this rank's GPU, so that the pinned host
-    buffers of the end-to-end leg (first touch) and the copy engines' DMA stay on the GPU's NUMA node.  Round 1
-    left every rank on the default policy and the 8-rank end-to-end step piled up on one socket's memory."""
+    """One process per GPU: run on the cores that are local to this rank's GPU and prefer that NUMA node for this
+    process's memory, so that the pinned host buffers of the end-to-end leg and the copy engines' DMA stay on the
+    GPU's side of the socket interconnect.  Round 1 left every rank on the default policy and the 8-rank end-to-end
+    step piled up on one socket's memory.  When the container's cpuset has no core on the GPU's node (an 8-GPU box
+    that hands out the cores of one socket only) the affinity cannot follow the GPU, but the memory policy still can:
+    set_mempolicy(MPOL_PREFERRED, node) -- it falls back silently when the node is not allowed."""
+    info = {"numa_cpus": None}
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -444,19 +448,35 @@ def bind_to_gpu_numa(local):
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:          # 00000000:1B:00.0 -> 0000:1b:00.0
             bus = bus[4:]
+        info["pci"] = bus
         with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
             spec = f.read().strip()
         cpus = set()
         for part in spec.split(","):
             a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+            if a:
+                cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
+        info["numa_cpus"] = len(cpus)
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return {"numa_cpus": len(cpus), "pci": bus}
+        node = -1
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238      # x86_64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 16 * 64 + 1)
+            info["mem_node"] = node if rc == 0 else "errno %d" % ctypes.get_errno()
     except Exception as e:       # no NUMA information: keep the default placement
-        return {"numa_cpus": None, "why": str(e)[:80]}
-    return {"numa_cpus": None}
+        info["why"] = str(e)[:80]
+    return info
 
 
 def hbm_peak():
@@ -534,6 +554,7 @@ def run_b200(args):
         sol.dostep_host(Qh, 0.0, nsteps=1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_local_s = e2e_s
 
     vals = [r["ms"], e2e_s, float(r["kern_ms"]), sustained["ms"] if sustained else 0.0,
             float(clk["sm_mhz"] or 0.0)]
@@ -544,7 +565,8 @@ def run_b200(args):
     if world > 1:
         allc = [None] * world
         dist.all_gather_object(allc, {"rank": rank, "sm_mhz": clk["sm_mhz"], "power_w_max": clk.get("power_w_max"),
-                                      "reasons": clk["reasons"], "kernel_ms_per_stage": r["kern_ms"] / (nstage * args.steps)})
+                                      "reasons": clk["reasons"], "kernel_ms_per_stage": r["kern_ms"] / (nstage * args.steps),
+                                      "host_placement": numa, "e2e_ms_per_step": e2e_local_s / e2e_steps * 1e3})
         clocks_per_rank = allc
 
     # ---- full-size parity + same-mesh CPU baseline (N = 1) ----------------------------------------
