@@ -488,6 +488,26 @@ __device__ __forceinline__ void extended_sources(const AtmosParams<R> &P, const 
   }
 }
 
+// xi3 part of the weak derivative for one (i-plane, state): out3[j][c] = sum_n D[n][c] F3[i + Nq j + Nq^2 n],
+// in place.  F3 = &S.F3[state][i]; every plane is read and rewritten by its own lane only.
+template <class R, int NQ>
+__device__ __forceinline__ void contract_xi3(R *F3) {
+#pragma unroll
+  for (int b = 0; b < NQ; ++b) {
+    R f[NQ], o[NQ];
+#pragma unroll
+    for (int n = 0; n < NQ; ++n) f[n] = F3[NQ * b + NQ * NQ * n];
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) {
+      o[c] = R(0);
+#pragma unroll
+      for (int n = 0; n < NQ; ++n) o[c] += const_D<R>(n * NQ + c) * f[n];
+    }
+#pragma unroll
+    for (int c = 0; c < NQ; ++c) F3[NQ * b + NQ * NQ * c] = o[c];
+  }
+}
+
 template <class R, int NQ, int NF1, bool AUX, bool VISC, bool SRCX>
 #ifndef CMDG_VISC_MINBLOCKS
 #define CMDG_VISC_MINBLOCKS 4
@@ -513,6 +533,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   constexpr bool FALIGN = CMDG_FACE_ALIGNED && (NFP <= 32) && (6 % (NWARP - 1) == 0);
   constexpr int NITEM = FALIGN ? 6 / (NWARP - 1) : (NFN + FSTRIDE - 1) / FSTRIDE;   // face items per face thread
   static_assert(NWARP >= 2 && NQ * 5 <= 32, "plane contraction: one warp holds Nq x 5 (plane, state) pairs");
+#ifndef CMDG_SPLIT_XI3
+#define CMDG_SPLIT_XI3 1
+#endif
+  // dense packing, three face warps: the third one has items in the first round only
+  constexpr bool SPLIT_XI3 = CMDG_SPLIT_XI3 && !FALIGN && NWARP == 4 && NFN > 2 * 32 && NFN <= 2 * FSTRIDE - 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TendSmem<R, NQ, AUX, VISC> &S = *reinterpret_cast<TendSmem<R, NQ, AUX, VISC> *>(smem_raw);
 
@@ -773,22 +798,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
       for (int b = 0; b < NQ; ++b)
 #pragma unroll
         for (int a = 0; a < NQ; ++a) F1[a + NQ * b] = pa[b][a];
-      // xi3: out3[j][c] = sum_n D[n][c] F3[i + Nq j + Nq^2 n] in the plane i = pk
-      R *F3 = &S.F3[ps][pk];
-#pragma unroll
-      for (int b = 0; b < NQ; ++b) {
-        R f[NQ], o[NQ];
-#pragma unroll
-        for (int n = 0; n < NQ; ++n) f[n] = F3[NQ * b + NQ * NQ * n];
-#pragma unroll
-        for (int c = 0; c < NQ; ++c) {
-          o[c] = R(0);
-#pragma unroll
-          for (int n = 0; n < NQ; ++n) o[c] += const_D<R>(n * NQ + c) * f[n];
-        }
-#pragma unroll
-        for (int c = 0; c < NQ; ++c) F3[NQ * b + NQ * NQ * c] = o[c];
-      }
+      if (!SPLIT_XI3) contract_xi3<R, NQ>(&S.F3[ps][pk]);
     }
   } else {
   // ---- faces: numerical flux at every face node of this element ----
@@ -901,6 +911,11 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 #pragma unroll
     for (int s = 0; s < 5; ++s) S.Qp[s][it] = sMvMI * fl[s];
   }
+  // the last face warp has one round of face items where the others have two: it takes the xi3 contraction
+  // (F3 planes, untouched by anybody else between the two barriers) off the contraction warp, whose dependent
+  // shared-load -> DFMA chain was the longest path between the barriers (ncu: 13 % of the warp samples were
+  // barrier stalls; warp instructions between the barriers 600 / 500 / 500 / 250 before, 400 / 500 / 500 / 450 now)
+  if (SPLIT_XI3 && fw == NWARP - 2 && lane < NQ * 5) contract_xi3<R, NQ>(&S.F3[lane / NQ][lane % NQ]);
   }
   __syncthreads();
 
