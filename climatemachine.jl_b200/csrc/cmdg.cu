@@ -795,6 +795,7 @@ TendArgs<R> base_args(cmdg_handle h) {
   a.F2 = (const R *)h->F2dev;
   a.Fn = (const R *)h->FnDev;
   a.nreal = (int)h->d.nrealelem;
+  a.nelem = (int)h->d.nelem;
   return a;
 }
 

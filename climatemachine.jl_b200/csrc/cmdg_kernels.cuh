@@ -82,6 +82,7 @@ struct TendArgs {
   const R *F2;         // [nelem][12][Np]   F2[d][s], s = 1..4, at column 4*d + s-1 (ghosts by exchange)
   const R *Fn;         // [nreal][6*Nfp][4] n . F2 at the element's own face nodes
   int nreal;
+  int nelem;           // real + ghost elements of Q (bulk-copy windows must stay inside the array)
   // tail prefetch: the last pfn_n[0] + pfn_n[1] blocks of this launch pull the inputs of the first
   // elements of the NEXT launch(es) into L2 (their first wave would otherwise start on cold DRAM misses:
   // the stage's output was written ~0.5 ms -- several L2 capacities -- earlier).  pfn_list[i] = launch
@@ -404,6 +405,31 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
+// Bulk (TMA engine) copy global -> shared with completion on an mbarrier: no registers, no LSU wavefronts.
+// dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(count)
+               : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *mbar) {
+  const unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(m)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned parity) {
+  const unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(m), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
 // Experiment, off by default (-DCMDG_FACE_AUX=1 builds it).  The plus-side geopotential and reference pressure of
 // a face node are constants of the grid (aux columns the model never changes after init): instead of gathering
 // them through L1 at every launch (2 of the 7 scattered 8-byte cp.async per face node plus their shared-memory
@@ -420,7 +446,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <class R, int NQ, bool AUX, bool VISC>
 struct TendSmem {
   static constexpr int NP = Dims<NQ>::NP, NFN = Dims<NQ>::NFN;
-  R Q[5][NP];                              // own state
+  // own state, [5][NP] starting at Qraw[0] or, when the element's first word is only 8-byte aligned in global
+  // memory and the state comes in by a bulk copy of the enclosing 16-byte aligned window, at Qraw[1]
+  alignas(16) R Qraw[5 * NP + 3];
+  unsigned long long mbar;                 // completion barrier of that bulk copy
   // contravariant fluxes M xi_m . F.  F12 is read by (k-plane, state) lanes, F3 by (i-plane,
   // state) lanes; the state stride of F3 is padded to 8 mod 16 + 5 doubles so that both are free of
   // bank conflicts (k-plane lanes: 25 k + 125 s, i-plane lanes: i + 133 s)
@@ -548,6 +577,31 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   const R *__restrict__ Qg = A.Q;
   const R *__restrict__ auxg = A.aux;
 
+  // ---- own state by ONE bulk copy (TMA engine) straight into shared memory: the five state columns of an element
+  // are 5 Np contiguous words, but only 8-byte aligned for every other element -- the copy takes the enclosing
+  // 16-byte aligned window (one extra word in front or behind) and the shared-memory view starts at word 0 or 1.
+  // Replaces five coalesced LDG + five STS per node thread by five LDS.  Measured (ncu, 61 440 elements, one box,
+  // profiles/r2_ncu_metrics_dg_tendency_tma_state*.csv): UBLKCP + SYNCS in the SASS, parity green, L1 data-pipe
+  // wavefronts 107.9 M -> 107.1 M, but 926 k -> 939 k cycles and 238.8 M -> 258.1 M warp instructions (the
+  // mbarrier try_wait spin and the extra block barrier that publishes the mbarrier), bench 68.4 -> 68.2 GDOF/s:
+  // a small net loss, so it is off by default (-DCMDG_TMA_Q=1 builds it).  Nothing else in this kernel can go
+  // through the bulk-copy engine with a gain: geometry, aux and the old tendency are consumed in registers (LDS
+  // would replace LDG one for one), and tensor-map copies of the face traces are impossible on the contractual
+  // layout (Np = 125 words per column: strides of 40 / 200 / 1000 bytes, not multiples of 16).
+#ifndef CMDG_TMA_Q
+#define CMDG_TMA_Q 0
+#endif
+  constexpr unsigned QWIN = (unsigned)((5 * NP + 1 + (16 / sizeof(R) - 1)) / (16 / sizeof(R)) * 16);   // bytes
+  const int qoff = (int)(eoffQ & (16 / sizeof(R) - 1));      // words in front of the element inside its window
+  const bool bulk = CMDG_TMA_Q && (((uintptr_t)Qg & 15) == 0) &&
+                    (eoffQ - qoff) * sizeof(R) + QWIN <= (size_t)A.nelem * P.nstate * NP * sizeof(R);
+  R *Qs = S.Qraw + (bulk ? qoff : 0);
+  if (CMDG_TMA_Q) {
+    if (tid == 0) mbar_init(&S.mbar, 1);
+    __syncthreads();
+    if (bulk && tid == 0) bulk_load_g2s(S.Qraw, Qg + (eoffQ - qoff), QWIN, &S.mbar);
+  }
+
   // ---- (a) face descriptors of my face items ----
   // Warp specialisation: after the node phase one warp (rotating with the block index, so
   // that the four schedulers share that work) contracts the fluxes with D plane by plane while
@@ -631,8 +685,10 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
   R xc[3] = {0, 0, 0};
   R f2[12];
   if (tid < NP) {
+    if (!bulk) {
 #pragma unroll
-    for (int s = 0; s < 5; ++s) q[s] = Qg[eoffQ + (size_t)s * NP + tid];
+      for (int s = 0; s < 5; ++s) q[s] = Qg[eoffQ + (size_t)s * NP + tid];
+    }
     if (AUX && SRCX) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) xc[d] = auxg[eoffA + (size_t)d * NP + tid];
@@ -685,11 +741,17 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
 
   // ---- (d) volume: fluxes at my node ----
   R src[5] = {0, 0, 0, 0, 0};
+  if (bulk) mbar_wait(&S.mbar, 0);     // every thread that later reads the state observes the completion itself
   if (tid < NP) {
+    if (bulk) {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) q[s] = Qs[s * NP + tid];
+    } else {
+#pragma unroll
+      for (int s = 0; s < 5; ++s) Qs[s * NP + tid] = q[s];
+    }
     const Thermo<R> th = thermo<R>(P, q, Phi);
     const R pflux = (AUX && P.subtract_off) ? th.p - pref : th.p;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) S.Q[s][tid] = q[s];
     S.P[tid] = th.p;
     S.Rinv[tid] = th.rinv;
     if (AUX) {
@@ -828,7 +890,7 @@ dg_tendency_kernel(const TendArgs<R> A, const AtmosParams<R> P) {
     }
     R qm[5], qp[5];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) qm[s] = S.Q[s][vm];
+    for (int s = 0; s < 5; ++s) qm[s] = Qs[s * NP + vm];
     Thermo<R> tm;
     tm.rinv = S.Rinv[vm];
     tm.p = S.P[vm];

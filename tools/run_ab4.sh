@@ -2,7 +2,7 @@
 # A/B: shipped build vs libcmdg$1.so (interleaved bench runs, ncu cycles), parity subset with the candidate,
 # and the ncu launch list of the timed loop (only libcmdg's kernels)
 BASE=${1:-_nosplit}
-python -m pytest tests -m gpu -q -x -k "vortex_tendency or baroclinic_wave_cubed or viscous_box_second or held_suarez_forcing or dry_biharmonic or tracers_as_shipped or vortex_float32" 2>&1 | tail -4
+python -m pytest tests -m gpu -q -x -k "vortex_tendency or baroclinic_wave_cubed or viscous_box_second or held_suarez_forcing or dry_biharmonic or tracers_as_shipped or float32 or rising_bubble or vortex_100 or plain_c_abi" 2>&1 | tail -4
 B="python bench.py --headline-only --no-parity --no-cpu-baseline --steps 100 --warmup 3"
 for rep in 1 2 3; do
 for v in "" $BASE; do
@@ -33,4 +33,4 @@ for v in ("","$BASE"):
     print("variant",v or "candidate")
     for k,vals in agg.items(): print("   ",k,vals)
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:cmdg --launch-skip 6 -c 40 --csv --log-file gpurun_out/final_launches.csv python bench.py --headline-only --no-parity --no-cpu-baseline --steps 4 --warmup 3 > /dev/null 2>&1; echo "launch list rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"dg_|lsrk|pack|scale_kernel" --launch-skip 8 -c 40 --csv --log-file gpurun_out/final_launches.csv python bench.py --headline-only --no-parity --no-cpu-baseline --steps 4 --warmup 3 > /dev/null 2>&1; echo "launch list rc=$?"
