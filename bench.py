@@ -579,6 +579,11 @@ def run_b200(args):
         if not args.no_cpu_baseline:
             cpu_b = cpu_baseline_from_host(P, case, host, args.workload, ne, nvert, args.cpu_budget)
         del host
+    elif world == 1 and ocean and not args.no_cpu_baseline:
+        try:
+            cpu_b = ocean_cpu_baseline(P, ne, nvert, args.cpu_budget)
+        except Exception as e:
+            cpu_b = {"error": str(e)[:200]}
 
     # ---- the other schedules / configs at the same N ---------------------------------------------
     ref_sched, secondary = None, None
@@ -612,6 +617,12 @@ def run_b200(args):
         del keep_grid
         torch.cuda.empty_cache()
         secondary["ocean_gyre"], _ = secondary_run(P, args, "ocean_gyre", rank, world, dev, dist, max(2, ssteps // 4))
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                secondary["ocean_gyre"]["cpu_baseline"] = ocean_cpu_baseline(
+                    P, *default_mesh("ocean_gyre", 1, args), min(args.cpu_budget, 8.0))
+            except Exception as e:      # the baseline is reported beside the GPU number, never in its way
+                secondary["ocean_gyre"]["cpu_baseline"] = {"error": str(e)[:200]}
         secondary["rising_bubble_tracers"], _ = secondary_run(P, args, "rising_bubble", rank, world, dev, dist,
                                                               max(2, ssteps // 4))
 
@@ -773,12 +784,92 @@ def cpu_baseline_from_host(P, case, host, workload, ne, nvert, budget_s):
             "ms_per_step": el / n * 1e3}
 
 
+def ocean_twin(P, ne, nvert):
+    """The C/OpenMP restatement of the reference's HBModel schedule (oracle/c/hb_ref.c) on the GPU arm's N = 1
+    ocean mesh and initial state (built on the host by the package's builders): (twin, Q, aux, dt, tableau)."""
+    import numpy as np
+    from oracle import cref
+    from climatemachine_jl_b200 import atmos_init as ai, balance_laws as bl
+    from climatemachine_jl_b200.dgmodel import _LSRK144
+    grid, prob = build_grid(P, "ocean_gyre", ne, nvert, 0, 1, "cpu")
+    m = P.HBModel(prob, cʰ=float(np.sqrt(9.81 * prob.H)))
+    Q0, aux = ai.ocean_gyre_state(prob, grid)
+    vel = {1: "noslip", 2: "freeslip", 3: "penetrable_freeslip", 4: "kinematic_stress"}
+    temp = {1: "insulating", 2: "temperature_flux"}
+    bcs = [(vel[v], temp[t]) for v, t in (bl.ocean_bc_codes(bc) for bc in prob.boundary_conditions)]
+    Pm = cref.hb_params_from(m.param_set.grav, m.ρₒ, m.cʰ, m.cᶻ, m.αᵀ, m.νʰ, m.νᶻ, m.κʰ, m.κᶻ, m.κᶜ, m.fₒ, m.β,
+                             prob.Lʸ, prob.τₒ, prob.λʳ, prob.θᴱ, bcs, grid.nvertelem)
+    npy = lambda t: np.ascontiguousarray(t.cpu().numpy())
+    c = cref.CRefHB(Pm, npy(grid.vgeo), npy(grid.sgeo), npy(grid.vmapM), npy(grid.vmapP), npy(grid.elemtobndy),
+                    grid.D_host, npy(grid.Imat).T, P.CutoffFilter(grid, 3).filter_matrix,
+                    P.ExponentialFilter(grid, 1, 8).filter_matrix, grid.nrealelem)
+    rka = np.array([float(x) for x in _LSRK144[0]])
+    rkb = np.array([float(x) for x in _LSRK144[1]])
+    return c, npy(Q0), npy(aux.data), 55.0, (rka, rkb), grid.nrealelem
+
+
+def ocean_cpu_baseline(P, ne, nvert, budget_s):
+    """`cpu_baseline` of the ocean workload: LSRK144 steps of the twin, all host threads, until the budget is used."""
+    from oracle import cref
+    c, Q, aux, dt, (rka, rkb), nreal = ocean_twin(P, ne, nvert)
+    cores = cref.use_all_cores_hb()
+    dQ = Q * 0
+    c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 1)          # warm-up (page faults, thread pool)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 1)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 50:
+            break
+    dof = nreal * NP * 4
+    return {"value": dof * 14 * n / el / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "port", "same_config": True,
+            "sample": (f"ocean_gyre: {ne} x {ne} x {nvert} elements ({nreal} elements, {dof} DOF) -- the GPU arm's N = 1 "
+                       f"mesh and initial state --, {n} LSRK144 steps (14 evaluations each) in {el:.1f} s; C/OpenMP "
+                       "restatement of the reference's HBModel schedule (oracle/c/hb_ref.c: vertical filters, gradient "
+                       "pass, stack integrals, tendency)"),
+            "ms_per_step": el / n * 1e3}
+
+
+def run_reference_ocean(args):
+    """`--impl reference --workload ocean_gyre`: the ocean twin, one LSRK144 step per bench step."""
+    import __graft_entry__ as ge
+    from oracle import cref
+    P = ge.load_package()
+    ne, nvert = default_mesh("ocean_gyre", 1, args)
+    c, Q, aux, dt, (rka, rkb), nreal = ocean_twin(P, ne, nvert)
+    cores = cref.use_all_cores_hb()
+    dQ = Q * 0
+    c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, max(args.warmup, 1))
+    t0 = time.perf_counter()
+    c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, args.steps)
+    el = time.perf_counter() - t0
+    dof = nreal * NP * 4
+    value = dof * 14 * args.steps / el / 1e9
+    sample = (f"one LSRK144 step (14 evaluations) per bench step on the GPU arm's N=1 ocean mesh; C/OpenMP restatement "
+              f"of the reference's HBModel schedule (Julia is not available; oracle/c/hb_ref.c), {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC,
+        "value": value, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": el / args.steps * 1e3,
+        "lsrk54_steps_per_s": args.steps / el, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name("ocean_gyre", ne, nvert, 1), "hyperdiffusion": "off",
+                   "nelem_total": int(nreal), "dof_total": int(dof),
+                   "skip_zero_viscosity": False, "parallelism": f"OpenMP x{cores}"},
+        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
 def run_reference(args):
     """`--impl reference`: the restated reference CPU path on the GPU arm's own mesh (ne = 32 x 10 by
     default; the mesh is built on the host by the package's vectorised builder), all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "ocean_gyre":
+        return run_reference_ocean(args)
     import numpy as np
     import __graft_entry__ as ge
     from oracle import cref

@@ -2,7 +2,8 @@
 
 THIS PACKAGE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-It is a NumPy (and, under ``oracle/c``, plain C) restatement of the reference
+It is a NumPy (and, under ``oracle/c``, plain C: ``dg_ref.c`` for the dry AtmosModel, ``hb_ref.c`` for the
+ocean HBModel, both checked against the NumPy code in ``tests/test_oracle_c.py``) restatement of the reference
 algorithm (CliMA/ClimateMachine.jl v0.3.0-DEV, pure Julia) for the single hot
 path named by BASELINE.json.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it,

@@ -168,3 +168,98 @@ class CRefDG:
                              _p(g.vmapM), _p(g.vmapP), _p(g.elemtobndy), _p(self.D), _p(self.elems),
                              C.c_int64(g.nreal), C.c_double(dt), C.c_int(len(a)), _p(a), _p(b),
                              C.c_int64(nsteps))
+
+
+# ---------------------------------------------------------------------------------------
+# ocean HydrostaticBoussinesqModel twin (oracle/c/hb_ref.c)
+# ---------------------------------------------------------------------------------------
+_SO_HB = os.path.join(_HERE, "c", "libhbref.so")
+_lib_hb = None
+
+
+class hb_params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("grav", "rho0", "ch", "cz", "alphaT", "nuh", "nuz", "kappah", "kappaz",
+                                          "kappac", "f0", "beta", "Ly", "tau0", "lambda_r", "thetaE")] + \
+               [("bc_vel", C.c_int32 * 6), ("bc_temp", C.c_int32 * 6), ("nf_first", C.c_int32), ("nvert", C.c_int32)]
+
+
+HB_VEL = {"noslip": 1, "freeslip": 2, "penetrable_freeslip": 3, "kinematic_stress": 4}
+HB_TEMP = {"insulating": 1, "temperature_flux": 2}
+
+
+def lib_hb():
+    global _lib_hb
+    if _lib_hb is None:
+        if not os.path.exists(_SO_HB):
+            raise RuntimeError(f"{_SO_HB} missing: run `make -C oracle/c` (done by __graft_entry__.build())")
+        _lib_hb = C.CDLL(_SO_HB)
+        _lib_hb.hb_set_num_threads.argtypes = [C.c_int]
+    return _lib_hb
+
+
+def hb_params_from(grav, rho0, ch, cz, alphaT, nuh, nuz, kappah, kappaz, kappac, f0, beta, Ly, tau0, lambda_r,
+                   thetaE, bcs, nvert, nf="rusanov"):
+    """hb_params from plain numbers; ``bcs``: per boundary tag a (velocity, temperature) pair of names."""
+    P = hb_params()
+    for k, v in dict(grav=grav, rho0=rho0, ch=ch, cz=cz, alphaT=alphaT, nuh=nuh, nuz=nuz, kappah=kappah,
+                     kappaz=kappaz, kappac=kappac, f0=f0, beta=beta, Ly=Ly, tau0=tau0, lambda_r=lambda_r,
+                     thetaE=thetaE).items():
+        setattr(P, k, float(v))
+    for i, (vel, temp) in enumerate(bcs):
+        P.bc_vel[i], P.bc_temp[i] = HB_VEL[vel], HB_TEMP[temp]
+    P.nf_first = {"rusanov": 0, "central": 1}[nf]
+    P.nvert = int(nvert)
+    return P
+
+
+def hb_params_from_model(model, nvert, nf="rusanov"):
+    """hb_params of an oracle HBModel over an OceanGyre problem."""
+    pr = model.problem
+    return hb_params_from(model.grav, model.rho0, model.ch, model.cz, model.alphaT, model.nuh, model.nuz,
+                          model.kappah, model.kappaz, model.kappac, model.f0, model.beta, pr.Ly, pr.tau0,
+                          pr.lambda_r, pr.thetaE, model.bcs, nvert, nf)
+
+
+class CRefHB:
+    """Reference-schedule HBModel tendency / LSRK steps on one rank (float64, N = 4, no ghost elements)."""
+
+    def __init__(self, P, vgeo, sgeo, vmapM, vmapP, elemtobndy, D, Imat, Fc, Fe, nreal):
+        self.P, self.nreal = P, int(nreal)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        self.vgeo, self.sgeo, self.D, self.Imat = f64(vgeo), f64(sgeo), f64(D), f64(Imat)
+        eye = np.eye(5)
+        self.Fc, self.Fe = f64(eye if Fc is None else Fc), f64(eye if Fe is None else Fe)
+        self.vmapM, self.vmapP, self.bnd = i64(vmapM), i64(vmapP), i64(elemtobndy)
+        assert self.vgeo.shape[0] == self.nreal, "the ocean twin runs one rank without ghost elements"
+        assert self.nreal % P.nvert == 0
+        self.gradflux = np.zeros((self.nreal, 10, 125))
+
+    @classmethod
+    def from_grid(cls, model, g, nf="rusanov"):
+        return cls(hb_params_from_model(model, g.topology.stacksize, nf), g.vgeo, g.sgeo, g.vmapM, g.vmapP,
+                   g.elemtobndy, g.D[0], g.Imat[2], model.vert_filter, model.exp_filter, g.nreal)
+
+    def _args(self):
+        return (_p(self.vgeo), _p(self.sgeo), _p(self.vmapM), _p(self.vmapP), _p(self.bnd), _p(self.D),
+                _p(self.Imat), _p(self.Fc), _p(self.Fe), C.c_int64(self.nreal))
+
+    def tendency(self, dQ, Q, aux, alpha=1.0, beta=0.0):
+        """In place: Q is filtered, aux gets w / pkin / wz0, self.gradflux the gradient flux."""
+        lib_hb().hb_ref_tendency(C.byref(self.P), _p(dQ), _p(Q), _p(aux), _p(self.gradflux), *self._args(),
+                                 C.c_double(alpha), C.c_double(beta))
+
+    def lsrk_steps(self, Q, dQ, aux, dt, rka, rkb, nsteps):
+        a = np.ascontiguousarray(rka, dtype=np.float64)
+        b = np.ascontiguousarray(rkb, dtype=np.float64)
+        lib_hb().hb_ref_lsrk_steps(C.byref(self.P), _p(Q), _p(dQ), _p(aux), _p(self.gradflux), *self._args(),
+                                   C.c_double(dt), C.c_int(len(a)), _p(a), _p(b), C.c_int64(nsteps))
+
+
+def use_all_cores_hb():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib_hb().hb_set_num_threads(n)
+    return n

@@ -161,3 +161,65 @@ def test_extended_precision_twin_and_conditioning():
         res[name] = rl(d[:g.nreal], t[:g.nreal])
     assert res["unbalanced"] < 1e-14, res
     assert 1e-13 < res["balanced"] < 1e-11, res
+
+
+def test_c_twin_ocean_hbmodel():
+    """The ocean twin (oracle/c/hb_ref.c: vertical filters, gradient pass with the convective-adjustment switch,
+    stack integrals, Rusanov + central second-order fluxes, flux-based ocean boundary conditions, LSRK144) against
+    the NumPy oracle, which reproduces the reference's ocean-gyre regression values (tests/test_oracle_ocean.py).
+    This is what gives BASELINE.json configs[4] a CPU baseline in bench.py."""
+    model, gs, prob = parity.ocean_setup(1, (4, 3, 3))
+    g = gs[0]
+    dgm = odg.DGModel(model, [g], "rusanov")
+    q = odg.init_ode_state(dgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    sol = oode.LSRK144NiegemannDiehlBusch(dgm, q, dt=120.0)
+    oode.solve(q, sol, numberofsteps=2)           # spin-up: w, pkin, wind stress, convective adjustment active
+    c = cref.CRefHB.from_grid(model, g, "rusanov")
+    cq, caux = q[0].data.copy(), dgm.state_auxiliary[0].data.copy()
+    cdq = np.full_like(cq, np.nan)
+    dq = [q[0].similar()]
+    dgm(dq, q, 0.0, 1, 0)
+    c.tendency(cdq, cq, caux, 1.0, 0.0)
+    assert parity.rel_l2(cq, q[0].data) < 1e-14                       # filtered in place
+    assert parity.rel_l2(c.gradflux, dgm.state_gradient_flux[0].data) < 1e-13
+    assert parity.rel_l2(caux[:, 1:4], dgm.state_auxiliary[0].data[:, 1:4]) < 1e-13
+    assert parity.rel_l2(cdq, dq[0].data) < 1e-13
+    # increment form, then two LSRK144 steps from the same state
+    dgm(dq, q, 0.0, 0.5, 2.0)
+    c.tendency(cdq, cq, caux, 0.5, 2.0)
+    assert parity.rel_l2(cdq, dq[0].data) < 1e-13
+    sol2 = oode.LSRK144NiegemannDiehlBusch(dgm, q, dt=120.0)
+    oode.solve(q, sol2, numberofsteps=2)
+    cdq[...] = 0
+    c.lsrk_steps(cq, cdq, caux, 120.0, sol2.RKA, sol2.RKB, 2)
+    assert parity.rel_l2(cq, q[0].data) < 1e-13
+
+
+def test_bench_ocean_twin_runs_on_package_arrays():
+    """bench.py's ocean CPU baseline: the C twin over the PACKAGE's host-built ocean mesh, initial state, filter
+    matrices and stack-integral operator (the arrays the GPU arm hands to libcmdg), a small box, two LSRK144 steps;
+    and the same state stepped by the NumPy oracle on the oracle's own mesh of that box."""
+    import bench
+    P = ge.load_package()
+    c, Q, aux, dt, (rka, rkb), nreal = bench.ocean_twin(P, 3, 3)
+    assert nreal == 27 and Q.shape == (27, 4, 125)
+    Q0 = Q.copy()
+    dQ = np.zeros_like(Q)
+    c.lsrk_steps(Q, dQ, aux, dt, rka, rkb, 2)
+    assert np.isfinite(Q).all() and np.isfinite(aux).all()
+    assert np.abs(Q - Q0).max() > 0
+    # the NumPy oracle on its own mesh of the same box (bench.py: Lx = Ly = 4e6 m, H = 1000 m at N = 1)
+    from oracle import ocean as oocean, topologies as otp, grids as ogrids
+    Lx, Ly, H = 4e6, 4e6, 1000.0
+    br = (np.linspace(0, Lx, 4), np.linspace(0, Ly, 4), np.linspace(-H, 0, 4))
+    topos = otp.StackedBrickTopology(1, br, periodicity=(False, False, False), boundary=((1, 1), (1, 1), (2, 3)))
+    g = ogrids.Grid(topos[0], 4)
+    prob = oocean.OceanGyre(Lx, Ly, H)
+    xi = g.xi[2]
+    model = oocean.HBModel(prob, vert_filter=oocean.cutoff_filter_matrix(xi, 3),
+                           exp_filter=oocean.exponential_filter_matrix(xi, 1, 8))
+    dgm = odg.DGModel(model, [g], "rusanov")
+    q = odg.init_ode_state(dgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3), 0.0)
+    sol = oode.LSRK144NiegemannDiehlBusch(dgm, q, dt=dt)
+    oode.solve(q, sol, numberofsteps=2)
+    assert parity.rel_l2(Q, q[0].data) < 1e-12
