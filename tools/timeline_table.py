@@ -81,5 +81,57 @@ def main():
             print(f"| {rank} | {t['interior']:.1f} | {t['int_gap']:.1f} | {t['ext_kernel']:.1f} | {t['pack'] + t['unpack']:.1f} | {t['nccl']:.1f} |")
 
 
+FAMILY = {1: "filter", 2: "gradient", 3: "column", 4: "tendency"}
+
+
+def ocean_main():
+    """`timeline_table.py --ocean <prefix>`: the HBModel marks carry `kernel family * 1e8 + elements` in `info`
+    (hb_eval_t).  Prints, per rank and for the middle stage of the last recorded step, every kernel / halo phase with
+    begin, end and duration, and the per-family sums over the whole step."""
+    prefix = sys.argv[2]
+    files = sorted(glob.glob(prefix + ".rank*.csv"))
+    print(f"# Ocean stage timeline, {len(files)} rank(s), last recorded step (microseconds)\n")
+    for f in files:
+        rank = f.split(".rank")[-1].split(".")[0]
+        st = load(f)
+        stages = sorted(st)
+        mid = stages[len(stages) // 2]
+        print(f"## rank {rank}, stage {mid + 1} of {len(stages)}\n")
+        print("| phase | elements / values | begin | end | us |")
+        print("|---|---|---|---|---|")
+        marks = st[mid]
+        opened = {}
+        rows = []
+        for lab, info, t in marks:
+            if lab == "kernel_begin":
+                opened[info] = t
+            elif lab == "kernel_end" and info in opened:
+                rows.append((opened.pop(info), t, FAMILY.get(info // 100000000, "kernel"), info % 100000000))
+        t_of = lambda name: [t for (l, i, t) in marks if l == name]
+        for b, e in zip(t_of("nccl_begin"), t_of("nccl_end")):
+            rows.append((b, e, "NCCL send/recv", 0))
+        for b, e in zip(t_of("unpack_begin"), t_of("unpack_end")):
+            rows.append((b, e, "unpack", 0))
+        for (l, i, t) in marks:
+            if l == "pack_end":
+                rows.append((t, t, "pack done", i))
+        for b, e, name, n in sorted(rows):
+            print(f"| {name} | {n or ''} | {b:.0f} | {e:.0f} | {e - b:.0f} |")
+        tot = defaultdict(float)
+        for s_ in stages:
+            op = {}
+            for lab, info, t in st[s_]:
+                if lab == "kernel_begin":
+                    op[info] = t
+                elif lab == "kernel_end" and info in op:
+                    tot[FAMILY.get(info // 100000000, "kernel")] += t - op.pop(info)
+        t_all = [t for s_ in stages for (_, _, t) in st[s_]]
+        print(f"\nstep: {max(t_all) - min(t_all):.0f} us over {len(stages)} stages; kernel sums per family: "
+              + ", ".join(f"{k} {v:.0f}" for k, v in sorted(tot.items())) + "\n")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--ocean":
+        ocean_main()
+    else:
+        main()
