@@ -913,7 +913,10 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(workload, ne, nvert, 1), "hyperdiffusion": "off",
                    "nelem_total": int(nreal), "dof_total": int(dof),
-                   "skip_zero_viscosity": bool(skip), "parallelism": f"OpenMP x{cores}"},
+                   "skip_zero_viscosity": bool(skip), "parallelism": f"OpenMP x{cores}",
+                   "sample_of": (None if args.gpus == 1 else
+                                 f"one GPU's share of the {args.gpus}-GPU weak-scaling mesh (ne = {WEAK_NE.get(args.gpus, '?')}): "
+                                 f"the N = 1 mesh has the same elements per GPU")},
         "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
