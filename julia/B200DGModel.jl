@@ -41,7 +41,7 @@ import ..ODESolvers
 import ..ODESolvers: dostep!, AbstractODESolver, LowStorageRungeKutta2N,
                      LSRK54CarpenterKennedy, LSRK144NiegemannDiehlBusch
 
-export B200DGModel, B200LSRK
+export B200DGModel, B200LSRK, dostep_host!
 
 const libcmdg = "libcmdg.so"
 
@@ -377,6 +377,18 @@ function dostep!(Q, s::B200LSRK, p, time, slow_δ = nothing, slow_rv_dQ = nothin
         b.handle, pointer(Q.data), pointer(l.dQ.data), time, l.dt, length(s.rka),
         s.rka, s.rkb, s.rkc, 1, CUDA.stream().handle))
     CUDA.synchronize()
+end
+# The same step through a HOST copy of `realview(Q)` (a plain `Array{FT,3}` of size Np x nstate x nrealelem, ideally
+# page-locked with `CUDA.Mem.pin`): what a driver that keeps its prognostic state on the CPU between steps calls, and
+# what bench.py times as `e2e`.  `cmdg_lsrk_steps_host` uploads, steps and downloads (on one rank the Euler path
+# overlaps the upload with the first stage and the download with the last one) and synchronises before it returns.
+function dostep_host!(Qhost::Array, s::B200LSRK, time::Real; nsteps::Integer = 1)
+    l = s.inner
+    b = l.rhs!::B200DGModel
+    GC.@preserve Qhost check(b.handle, ccall((:cmdg_lsrk_steps_host, libcmdg), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+        b.handle, pointer(Qhost), time, l.dt, length(s.rka), s.rka, s.rkb, s.rkc, nsteps))
+    return Qhost
 end
 # the nsubsteps wrapper used by multirate solvers (LowStorageRungeKuttaMethod.jl:73-89)
 function dostep!(Q, s::B200LSRK, p, time::Real, nsubsteps::Int, iStage::Int,
