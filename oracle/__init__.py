@@ -33,7 +33,11 @@ the oracle is pinned against the reference's *own* golden numbers instead:
   (``tests/test_oracle_filters.py``, fixtures in ``tests/golden``);
 * ``test/Ocean/refvals/test_ocean_gyre_refvals.jl`` (short) and ``test_windstress_refvals.jl``
   (explicit_cpu) -- HBModel regression values (``tests/test_oracle_ocean.py``,
-  ``tests/test_oracle_ocean_windstress.py``); ``test/Numerics/DGMethods/integral_test.jl`` -- the stack
+  ``tests/test_oracle_ocean_windstress.py``); ``test/Ocean/HydrostaticBoussinesq/test_3D_spindown.jl`` with
+  ``refvals/3D_hydrostatic_spindown_refvals.jl`` (explicit) -- 720 LSRK144 steps of the SimpleBox spin-down
+  (periodic, free-slip / penetrable free-slip boundaries) by the C twin: statistics to 1.5e-12, and the error
+  against the analytic solution equal to the value the reference prints to 1e-14
+  (``tests/test_oracle_ocean_spindown.py``); ``test/Numerics/DGMethods/integral_test.jl`` -- the stack
   integral (``tests/test_oracle_integral.py``);
 * ``test/Numerics/ODESolvers/ode_tests_convergence.jl`` -- LSRK54 / LSRK144 order 4 on the reference's
   time-dependent problem;

@@ -85,6 +85,39 @@ class OceanGyre:
         return self.lambda_r * (theta - theta_r)
 
 
+class SimpleBox:
+    """``SimpleBox`` with ``Fixed`` rotation (``src/Ocean/OceanProblems/simple_box_problem.jl:96-236``): the
+    analytic barotropic + baroclinic spin-down of a standing gravity wave, no wind stress, no surface heat flux,
+    Coriolis parameter identically zero."""
+
+    tau0, lambda_r, thetaE = 0.0, 0.0, 0.0
+
+    def __init__(self, Lx, Ly, H):
+        self.Lx, self.Ly, self.H = float(Lx), float(Ly), float(H)
+
+    def init_state(self, x, y, z, t=0.0, model=None):
+        from scipy.linalg import expm
+        m = model
+        kx, kz = 2 * np.pi / self.Lx, 2 * np.pi / self.H
+        gH = m.grav * self.H
+        M = np.array([[-m.nuh * kx ** 2, gH * kx], [-kx, 0.0]])
+        A = expm(M * t) @ np.ones(2)
+        U = A[0] * np.sin(kx * x)
+        eta = A[1] * np.cos(kx * x)
+        lam = m.nuh * kx ** 2 + m.nuz * kz ** 2
+        u0 = np.exp(-lam * t) * np.cos(kz * z) * np.sin(kx * x)
+        Q = np.zeros((4,) + y.shape)
+        Q[0] = u0 + U / self.H
+        Q[2] = eta
+        return Q
+
+    def kinematic_stress(self, y, rho):
+        return [0 * y, 0 * y]
+
+    def surface_flux(self, y, theta):
+        return 0 * y
+
+
 class HBModel:
     """Pointwise physics + the model's update_auxiliary_state hooks."""
     S, A, Gn, GF = 4, 8, 5, 10

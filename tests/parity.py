@@ -816,3 +816,57 @@ def ocean_case_float32(nsteps=2, dt=120.0, nelem=(5, 5, 5), spinup=3):
     res["finite"] = bool(np.isfinite(gotQ).all())
     dg.close()
     return res
+
+
+def ocean_spindown_on_device(nsteps=720):
+    """test/Ocean/HydrostaticBoussinesq/test_3D_spindown.jl (explicit) run entirely through libcmdg: SimpleBox
+    spin-down (periodic in x and y, free-slip bottom, penetrable free-slip surface, insulating, c_h = 1, no buoyancy /
+    diffusion / rotation), 5 x 5 x 8 elements, `nsteps` LSRK144 steps of 120 s in one cmdg_lsrk_steps call.  Returns the
+    per-field statistics, the difference to the C twin of the oracle run on the same arrays, and the error against
+    the analytic solution (the reference prints 0.0011289879366523504)."""
+    from oracle import cref
+    from tests.test_oracle_ocean_spindown import spindown_setup
+    P = pkg()
+    model, g, prob = spindown_setup()
+    odgm = odg.DGModel(model, [g], "rusanov")
+    oQ = odg.init_ode_state(odgm, lambda x1, x2, x3, a, t: prob.init_state(x1, x2, x3, 0.0, model), 0.0)
+    dgrid = P.DiscontinuousSpectralElementGrid(
+        g.N[0], g.vgeo, g.sgeo, g.vmapM, g.vmapP, g.elemtobndy, g.D[0], g.nreal,
+        interiorelems=g.interiorelems, exteriorelems=g.exteriorelems,
+        nvertelem=g.topology.stacksize, Imat=g.Imat[2], xi=g.xi[2])
+    pbcs = (P.OceanBC(P.Impenetrable(P.FreeSlip()), P.Insulating()),
+            P.OceanBC(P.Penetrable(P.FreeSlip()), P.Insulating()))
+    m = P.HBModel(P.HomogeneousBox(prob.Lx, prob.Ly, prob.H, boundary_conditions=pbcs), cʰ=1.0, αᵀ=0.0, κʰ=0.0,
+                  κᶻ=0.0, fₒ=0.0, β=0.0)
+    aux = P.MPIStateArray(dgrid, 8, data=odgm.state_auxiliary[0].data)
+    md = dict(vert_filter=P.CutoffFilter(dgrid, 3), exp_filter=P.ExponentialFilter(dgrid, 1, 8))
+    dg = P.DGModel(m, dgrid, P.RusanovNumericalFlux(), P.CentralNumericalFluxSecondOrder(),
+                   P.CentralNumericalFluxGradient(), state_auxiliary=aux, modeldata=md)
+    dQ = P.MPIStateArray(dgrid, 4, data=oQ[0].data)
+    sol = P.LSRK144NiegemannDiehlBusch(dg, dQ, dt=120.0, t0=0.0)
+    P.solve(dQ, sol, numberofsteps=nsteps)
+    Qd = dQ.data.cpu().numpy()[:g.nreal]
+    auxd = dg.state_auxiliary.data.cpu().numpy()[:g.nreal]
+    # the C twin of the oracle on the same arrays
+    c = cref.CRefHB.from_grid(model, g, "rusanov")
+    cref.use_all_cores_hb()
+    cq, caux = oQ[0].data.copy(), odgm.state_auxiliary[0].data.copy()
+    osol = oode.LSRK144NiegemannDiehlBusch(odgm, oQ, dt=120.0)
+    c.lsrk_steps(cq, np.zeros_like(cq), caux, 120.0, osol.RKA, osol.RKB, nsteps)
+
+    def stats(v):
+        v = v.ravel()
+        mean = v.mean()
+        return v.min(), v.max(), mean, np.sqrt(np.sum((v - mean) ** 2) / (v.size - 1))
+    x = [g.vgeo[:, ogrids._x1], g.vgeo[:, ogrids._x2], g.vgeo[:, ogrids._x3]]
+    Qe = np.moveaxis(prob.init_state(x[0], x[1], x[2], 120.0 * nsteps, model), 0, 1)
+    M = g.vgeo[:, ogrids._M][:, None, :]
+    res = {"stats": {("Q", 0): stats(Qd[:, 0]), ("Q", 2): stats(Qd[:, 2]), ("aux", 1): stats(auxd[:, 1]),
+                     ("aux", 3): stats(auxd[:, 3])},
+           "state_vs_twin_rel_l2": rel_l2(Qd[:, [0, 2]], cq[:, [0, 2]]),
+           "aux_vs_twin_rel_l2": rel_l2(auxd[:, [1, 3]], caux[:, [1, 3]]),
+           "u2_max": float(np.abs(Qd[:, 1]).max()), "theta_max": float(np.abs(Qd[:, 3]).max()),
+           "error_vs_exact": float(np.sqrt(np.sum(M * (Qd - Qe) ** 2)) / np.sqrt(np.sum(M * Qe ** 2))),
+           "launches": dg.kernel_launches()}
+    dg.close()
+    return res
