@@ -17,7 +17,8 @@ the oracle is pinned against the reference's *own* golden numbers instead:
 * ``test/Numerics/DGMethods/Euler/isentropicvortex.jl:60-238`` -- L2 error table
   (mesh + metrics + DGModel + Rusanov/Central/Roe + LSRK54 + thermodynamic
   constants, end to end), reproduced to ``rtol = sqrt(eps)`` as the test itself
-  demands (``tests/test_oracle_golden.py``);
+  demands (``tests/test_oracle_golden.py``: levels 1-2 in NumPy; levels 3-4, Rusanov and Central, by the C twin
+  in ``tests/test_oracle_c.py``);
 * ``test/Numerics/DGMethods/compressible_Navier_Stokes/mms_bc_atmos.jl`` -- the second-order
   (Navier-Stokes) path: 3-D level-1 golden error to 1e-7 (``tests/test_oracle_mms.py``);
 * ``test/Numerics/DGMethods/advection_diffusion/periodic_3D_hyperdiffusion.jl`` -- the

@@ -223,3 +223,40 @@ def test_bench_ocean_twin_runs_on_package_arrays():
     sol = oode.LSRK144NiegemannDiehlBusch(dgm, q, dt=dt)
     oode.solve(q, sol, numberofsteps=2)
     assert parity.rel_l2(Q, q[0].data) < 1e-12
+
+
+@pytest.mark.parametrize("nf,level,golden", [
+    ("rusanov", 3, 2.0160333422867591e-02), ("rusanov", 4, 6.6360317881818034e-04),
+    ("central", 3, 1.1680141169828175e-01), ("central", 4, 2.6414127301659534e-03)])
+def test_c_twin_isentropic_vortex_golden_levels_3_4(nf, level, golden):
+    """The finer rows of the reference's isentropic-vortex error table (test/Numerics/DGMethods/Euler/
+    isentropicvortex.jl:103-111: 3-D Float64, levels 3 and 4 = 20 x 20 x 1 and 40 x 40 x 1 elements) reproduced by the
+    C twin -- the NumPy oracle pins levels 1 and 2 (tests/test_oracle_golden.py) and is too slow beyond.  Same recipe
+    as `test_run` (:306-442): dt = dx_min / c(300 K) / N^2 snapped to hit timeend = 2 L / 10 / 150, mass-weighted L2
+    distance to the translated vortex; the reference's own gate is rtol = sqrt(eps)."""
+    from oracle import topologies as otp, grids as ogrids, atmos as oat, mpistatearrays as msa
+    FT = np.float64
+    ps = oat.Params(FT)
+    setup = oat.IsentropicVortexSetup(ps, FT)
+    L = setup.domain_halflength
+    ne = 2 ** (level - 1) * 5
+    br = (np.linspace(-L, L, ne + 1), np.linspace(-L, L, ne + 1), np.linspace(-L, L, 2))
+    g = ogrids.Grid(otp.BrickTopology(1, br, periodicity=(True, True, True))[0], 4, FT=FT)
+    model = oat.DryAtmosModel(FT, orientation="none", ref_state=None, turbulence=("constant_dynamic", 0.0, False),
+                              sources=())
+    dgm = odg.DGModel(model, [g], nf, skip_zero_viscosity=True)
+    timeend = FT(2 * L / 10 / setup.translation_speed)
+    dt = min(float(np.min(np.diff(b))) for b in br) / oat.soundspeed_air(ps, setup.T_inf) / 4 ** 2
+    nsteps = int(np.ceil(timeend / dt))
+    dt = timeend / nsteps
+    init = lambda x1, x2, x3, a, t: setup(x1, x2, x3, FT(t))
+    q = odg.init_ode_state(dgm, init, 0)
+    sol = oode.LSRK54CarpenterKennedy(dgm, q, dt=dt, t0=0)
+    c = cref.CRefDG(model, g, nf)
+    cref.use_all_cores()
+    cq = q[0].data.copy()
+    c.lsrk_steps(cq, np.zeros_like(cq), dgm.state_auxiliary[0].data.copy(), float(dt), sol.RKA, sol.RKB, nsteps)
+    qe = odg.init_ode_state(dgm, init, timeend)
+    q[0].data[...] = cq
+    err = msa.euclidean_distance(q, qe)
+    assert err == pytest.approx(golden, rel=1e-8), (err, golden)
