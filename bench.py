@@ -189,17 +189,19 @@ def build_grid(P, workload, ne, nvert, rank, nranks, device):
         return gr.build_grid(topo, 4, torch.float64, tp.cubed_sphere_warp, device), None
     if workload == "ocean_gyre":
         # BASELINE.json configs[4]: OceanBoxGCM HBModel, 20 x 20 x 50 elements per GPU
-        # (experiments/OceanBoxGCM/homogeneous_box.jl:11-21), box widened in x with the GPU count
-        prob = P.OceanGyre(4e6 * nranks, 4e6, 1000.0)
-        br = (np.linspace(0, prob.Lˣ, ne * nranks + 1), np.linspace(0, prob.Lʸ, ne + 1),
+        # (experiments/OceanBoxGCM/homogeneous_box.jl:11-21), box replicated fx x fy times horizontally (weak_box)
+        fx, fy = weak_box(nranks)
+        prob = P.OceanGyre(4e6 * fx, 4e6 * fy, 1000.0)
+        br = (np.linspace(0, prob.Lˣ, ne * fx + 1), np.linspace(0, prob.Lʸ, ne * fy + 1),
               np.linspace(-prob.H, 0, nvert + 1))
         topo = tp.stacked_brick_topology(br, (False, False, False), ((1, 1), (1, 1), (2, 3)), rank, nranks)
         return gr.build_grid(topo, 4, torch.float64, None, device), prob
     if workload == "rising_bubble":
         # BASELINE.json configs[0] (tutorials/Atmos/risingbubble.jl) at benchmark size: 500 m elements, 10 km deep
-        # (20 levels as the tutorial), ne x ne/4 elements horizontally per GPU (the tutorial: 20 x 1), periodic x / y
-        br = (np.linspace(0, 500.0 * ne * nranks, ne * nranks + 1), np.linspace(0, 500.0 * max(ne // 4, 1), max(ne // 4, 1) + 1),
-              np.linspace(0, 10000.0, nvert + 1))
+        # (20 levels as the tutorial), ne x ne/4 elements horizontally per GPU (the tutorial: 20 x 1; weak_box copies), periodic x / y
+        fx, fy = weak_box(nranks)
+        nx, ny = ne * fx, max(ne // 4, 1) * fy
+        br = (np.linspace(0, 500.0 * nx, nx + 1), np.linspace(0, 500.0 * ny, ny + 1), np.linspace(0, 10000.0, nvert + 1))
         topo = tp.stacked_brick_topology(br, (True, True, False), ((0, 0), (0, 0), (1, 2)), rank, nranks)
         return gr.build_grid(topo, 4, torch.float64, None, device), None
     L = 0.05
@@ -353,6 +355,20 @@ def reduce_max_sum(vals, world, dev, dist):
     return [float(x) for x in tmax], [float(x) for x in tsum]
 
 
+def weak_box(world):
+    """Horizontal replication (fx, fy) of the per-GPU box for the weak-scaling series of the box workloads (ocean,
+    rising bubble): as square as a power of two allows -- 1 x 1, 2 x 1, 2 x 2, 4 x 2 for 1, 2, 4, 8 GPUs.  The
+    reference's partition is a Hilbert curve over the horizontal columns (kept, BrickMesh.jl:449-522): on a box that
+    only grows in x (round 2 until its last day: 160 x 20 columns at 8 GPUs) it cuts elongated, fragmented parts --
+    8 150 of 20 000 elements exterior and six neighbours on the worst rank, against 1 950 and three on the 2 x 2 box."""
+    fx = 1
+    while fx * fx < world:
+        fx *= 2
+    if world % fx:
+        return world, 1
+    return fx, world // fx
+
+
 def workload_name(workload, ne, nvert, world, hyper=False):
     if workload == "baroclinic_wave":
         return f"dry baroclinic wave, cubed sphere ne={ne} x {nvert} vertical, N=4, Rusanov, LSRK54, dt=0.4 s"
@@ -361,11 +377,13 @@ def workload_name(workload, ne, nvert, world, hyper=False):
                 "direction), sources Gravity/Coriolis/HeldSuarezForcing/RayleighSponge, cubed sphere "
                 f"ne={ne} x {nvert}, N=4, Rusanov, LSRK54, dt=0.4 s")
     if workload == "ocean_gyre":
-        return (f"OceanBoxGCM HBModel ocean gyre, {ne * world}x{ne}x{nvert} elements, N=4, Rusanov, LSRK144 "
+        fx, fy = weak_box(world)
+        return (f"OceanBoxGCM HBModel ocean gyre, {ne * fx}x{ne * fy}x{nvert} elements, N=4, Rusanov, LSRK144 "
                 "(a step = 14 stages), dt=55 s")
     if workload == "rising_bubble":
+        fx, fy = weak_box(world)
         return (f"rising thermal bubble LES (tutorials/Atmos/risingbubble.jl as shipped: SmagorinskyLilly, NTracers{{4}}, "
-                f"DryAdiabaticProfile), {ne * world}x{max(ne // 4, 1)}x{nvert} elements of 500 m, N=4, Rusanov, LSRK144 "
+                f"DryAdiabaticProfile), {ne * fx}x{max(ne // 4, 1) * fy}x{nvert} elements of 500 m, N=4, Rusanov, LSRK144 "
                 "(a step = 14 stages), dt=0.4 s")
     return f"isentropic vortex, periodic box {ne}^3, N=4, Rusanov, LSRK54"
 
