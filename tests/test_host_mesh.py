@@ -235,3 +235,25 @@ def test_partition_invariants_the_device_schedule_relies_on(nranks):
         looked_at = set(vp[vp >= g.nrealelem * Np].tolist())
         assert looked_at <= ghost_nodes                                   # (iv)
         assert len(looked_at) > 0
+
+
+def test_weak_scaling_boxes_partition_compactly():
+    """bench.py replicates the per-GPU box of the ocean / rising-bubble workloads as squarely as a power of two allows
+    (`weak_box`), because the reference's Hilbert partition (kept) cuts an x-only box into fragmented parts: the share
+    of exterior elements on the worst rank is what the overlapped schedules can hide the halo behind."""
+    import bench
+    import __graft_entry__ as ge
+    from climatemachine_jl_b200 import topologies as ptp
+    ge.load_package()
+    assert [bench.weak_box(w) for w in (1, 2, 4, 8)] == [(1, 1), (2, 1), (2, 2), (4, 2)]
+
+    def worst_exterior_share(nx, ny, world):
+        br = (np.linspace(0, 1.0 * nx, nx + 1), np.linspace(0, 1.0 * ny, ny + 1), np.linspace(-1.0, 0, 3))
+        worst = 0.0
+        for rank in range(world):
+            t = ptp.stacked_brick_topology(br, (False, False, False), ((1, 1), (1, 1), (2, 3)), rank, world)
+            worst = max(worst, len(t.exteriorelems) / t.nreal)
+        return worst
+    assert worst_exterior_share(160, 20, 8) > 0.40          # the x-only box of the 8-GPU ocean figure in DESIGN section 5
+    assert worst_exterior_share(80, 40, 8) < 0.23
+    assert worst_exterior_share(40, 40, 4) < 0.10
